@@ -1,0 +1,193 @@
+/*
+ * zrt.h — C ABI of libzrt, the B200-native path-tracing core for zraytrace scenes.
+ *
+ * This header is the drop-in boundary for ONE function of the reference:
+ *
+ *     pub fn render(allocator, random, camera: Camera, surfaces: ArrayList(Surface),
+ *                   render_params: RenderParams) !*Image          (src/raytrace.zig:136-138)
+ *
+ * Everything the reference does below that call (pixel/sample loop raytrace.zig:162-187, rayColor
+ * :62-100, BVH bvh.zig:187-205, sphere.zig:31-71, triangle.zig:48-70, material.zig:43-128,
+ * texture.zig:52-74) runs as hand-written sm_100a CUDA behind these entry points.  There is no CPU
+ * fallback: without a CUDA device every compute entry point returns ZRT_ERR_NO_DEVICE.
+ *
+ * Plain C, POD structs, caller-owned host buffers in and out, no C++/torch types.
+ * A Zig caller binds it exactly like the reference binds libpng (png_image.zig:6-9, build.zig:17-19):
+ *     const c = @cImport({ @cInclude("zrt.h"); });   exe.linkSystemLibrary("zrt");
+ */
+#ifndef ZRT_H
+#define ZRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZRT_ABI_VERSION 1
+
+/* ---- status codes (Zig error union of render() -> int; never throws/aborts across the ABI) ---- */
+enum {
+    ZRT_OK = 0,
+    ZRT_ERR_INVALID = -1,   /* bad argument / inconsistent scene description */
+    ZRT_ERR_NO_DEVICE = -2, /* no CUDA device: there is deliberately no CPU fallback */
+    ZRT_ERR_CUDA = -3,      /* a CUDA runtime call failed, see zrt_last_error() */
+    ZRT_ERR_OOM = -4,       /* host allocation failed (error.OutOfMemory in the reference) */
+    ZRT_ERR_IO = -5         /* asset file could not be read / written (host helpers only) */
+};
+
+/* ---- math PODs: vector.zig:22-26 (Vec3), base.zig:2 (BaseFloat = f32) ---- */
+typedef struct zrt_vec3 { float x, y, z; } zrt_vec3;
+
+/* ---- shapes ---- */
+/* sphere.zig:15-20.  Negative radius is legal and flips the normal (scenes.zig:96). */
+typedef struct zrt_sphere {
+    zrt_vec3 center;
+    float radius;
+    uint32_t material; /* index into zrt_scene_desc.materials (reference: *const Material) */
+} zrt_sphere;
+
+/* triangle.zig:15-30.  Only a,b,c are given; e1,e2,face_normal are derived as triangle.zig:32-44. */
+typedef struct zrt_triangle {
+    zrt_vec3 a, b, c;
+    uint32_t material;
+} zrt_triangle;
+
+/* surface.zig:12-15: the caller's ArrayList(Surface) in order.  The position in this list is the
+ * surface id reported by zrt_primary_hits and decides ties exactly like raytrace.zig:75-81. */
+enum { ZRT_SURFACE_SPHERE = 0, ZRT_SURFACE_TRIANGLE = 1 };
+typedef struct zrt_surface {
+    uint32_t kind;  /* ZRT_SURFACE_* */
+    uint32_t index; /* into spheres[] or triangles[] */
+} zrt_surface;
+
+/* ---- materials and textures ---- */
+/* material.zig:16-29 */
+enum { ZRT_MATERIAL_LAMBERTIAN = 0, ZRT_MATERIAL_METAL = 1, ZRT_MATERIAL_DIELECTRIC = 2 };
+typedef struct zrt_material {
+    uint32_t kind;             /* ZRT_MATERIAL_* */
+    uint32_t texture;          /* lambertian/metal: index into textures[]; ignored for dielectric */
+    float index_of_refraction; /* dielectric only (material.zig:99-103) */
+} zrt_material;
+
+/* texture.zig:7-16,30-50 */
+enum { ZRT_TEXTURE_COLOR = 0, ZRT_TEXTURE_IMAGE = 1 };
+typedef struct zrt_texture {
+    uint32_t kind;         /* ZRT_TEXTURE_* */
+    float r, g, b;         /* ColorTexture.color */
+    /* ImageTexture: 8-bit texels, `channels` (3 or 4) bytes per texel, row 0 = BOTTOM scanline,
+     * i.e. already flipped the way png_image.readFile stores it (png_image.zig:82-87).  The device
+     * converts byte/255.0f on lookup, bit-identical to png_image.zig:87. */
+    uint32_t width, height, channels;
+    const uint8_t *pixels;
+    float u_offset, v_offset; /* texture.zig:14-16 default (0.19, 0.1) */
+} zrt_texture;
+
+/* ---- the scene: what the reference passes as `surfaces` plus everything reachable from it ---- */
+typedef struct zrt_scene_desc {
+    uint32_t n_surfaces;   const zrt_surface *surfaces;
+    uint32_t n_spheres;    const zrt_sphere *spheres;
+    uint32_t n_triangles;  const zrt_triangle *triangles;
+    uint32_t n_materials;  const zrt_material *materials;
+    uint32_t n_textures;   const zrt_texture *textures;
+} zrt_scene_desc;
+
+/* camera.zig:11-15 (the result of Camera.init :17-35, computed by the caller on the host) */
+typedef struct zrt_camera {
+    zrt_vec3 origin, lower_left_corner, horizontal, vertical;
+} zrt_camera;
+
+/* raytrace.zig:102-108 RenderParams, widened to u32 (main.zig parses u16), plus the extensions the
+ * B200 path needs.  Zero in an extension field selects the reference behaviour. */
+enum { ZRT_XLIMIT_HEIGHT = 0, ZRT_XLIMIT_WIDTH = 1 };
+typedef struct zrt_params {
+    uint32_t width, height, samples_per_pixel, max_depth;
+    uint32_t bounded_volume_hierarchy; /* BVH is used iff this != 0 AND n_surfaces > 10 (raytrace.zig:127) */
+    /* --- extensions --- */
+    uint32_t x_limit;      /* ZRT_XLIMIT_HEIGHT reproduces `while (x < image.height)` raytrace.zig:168 */
+    uint64_t seed;         /* key of the counter-based RNG that replaces the shared PRNG (scenes.zig:60) */
+    uint32_t sample_begin; /* global sample range [begin,end) traced by this call; 0,0 = all */
+    uint32_t sample_end;   /*   (used to split samples-per-pixel across GPUs) */
+    uint32_t flags;        /* ZRT_FLAG_* */
+    uint32_t reserved;
+} zrt_params;
+
+enum {
+    ZRT_FLAG_RAW_SUM = 1u << 0, /* output the un-normalised sum over the traced samples (for multi-GPU
+                                   reduction) instead of sum * (1/samples_per_pixel) raytrace.zig:157,182 */
+    ZRT_FLAG_BVH_SAH = 1u << 1  /* traverse a binned-SAH tree built by libzrt instead of the flattened
+                                   reference tree; hits are identical (tie-break on reference DFS order) */
+};
+
+/* raytrace.zig:20-34 Progress (the six u64 counters), same semantics */
+typedef struct zrt_counters {
+    uint64_t recursion_depth_hits;
+    uint64_t reflections;
+    uint64_t background_hits;
+    uint64_t pixels_processed;
+    uint64_t samples_processed;
+    uint64_t rays_processed;
+} zrt_counters;
+
+/* device timings of the last call, milliseconds from CUDA events on the launching stream */
+typedef struct zrt_timing {
+    float prepare_ms; /* host flatten / BVH build + H2D upload ("Prepare runtime" raytrace.zig:200) */
+    float kernel_ms;  /* path-tracing kernel(s) only */
+    float resolve_ms; /* chunk sum + 1/spp scale */
+    float total_ms;   /* first launch to last D2H copy done */
+    uint32_t launches;/* kernels launched by this call */
+    uint32_t bvh_nodes;
+} zrt_timing;
+
+typedef struct zrt_scene zrt_scene; /* opaque: flattened scene resident in HBM of one device */
+
+/* ---- entry points ---- */
+
+/* Number of CUDA devices visible (0 = none; compute entry points will fail with ZRT_ERR_NO_DEVICE). */
+int zrt_device_count(void);
+
+/* Message of the last error on the calling thread ("" if none). */
+const char *zrt_last_error(void);
+
+/* Copy + flatten the caller's surface list (raytrace.zig:150 preprocessSufraces, bvh.zig:171-185)
+ * and upload it to `device`.  The description may be freed as soon as this returns. */
+int zrt_scene_create(const zrt_scene_desc *desc, int device, zrt_scene **out);
+void zrt_scene_destroy(zrt_scene *scene);
+
+/* raytrace.render(): out_rgb is width*height*3 floats, pixel (x,y) at (y*width+x)*3, row 0 = bottom
+ * scanline (image.zig:74-103 as written by raytrace.zig:180-182).  counters/timing may be NULL. */
+int zrt_render(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
+               float *out_rgb, zrt_counters *counters, zrt_timing *timing);
+
+/* Same work, but results stay on the device: d_rgb (width*height*3 floats) and d_counters (6 u64)
+ * are DEVICE pointers on the scene's device, `stream` is a cudaStream_t (NULL = default stream).
+ * Asynchronous: returns after the launches are enqueued.  This is what the multi-GPU driver uses so
+ * that the accumulators can be summed with one NCCL reduce without touching the host. */
+int zrt_render_device(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
+                      float *d_rgb, uint64_t *d_counters, void *stream);
+
+/* Parity AOV: first iteration of rayColor (raytrace.zig:71-81) for every pixel.  surface_id[y*w+x] is
+ * the index in desc.surfaces of the closest hit (0xFFFFFFFF = background), t its ray parameter.
+ * jitter = 0 traces (u,v) = ((x-0.5)/w,(y-0.5)/h), i.e. raytrace.zig:173-174 with xi = 0;
+ * jitter = 1 uses the RNG draw of sample index params->sample_begin. */
+#define ZRT_NO_HIT 0xFFFFFFFFu
+int zrt_primary_hits(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
+                     int jitter, uint32_t *surface_id, float *t);
+
+/* Statistics of the flattened acceleration structure (0 nodes when the list path is used). */
+typedef struct zrt_bvh_info {
+    uint32_t nodes, leaves, max_depth, pruned_surfaces;
+} zrt_bvh_info;
+int zrt_scene_bvh_info(zrt_scene *scene, uint32_t flags, zrt_bvh_info *out);
+
+/* K0 microbenchmarks that measure the roofline denominators this path is judged against
+ * (MEASURED_PEAKS.json has no FP32-issue or L2 number): results in out[0..n).
+ *   out[0] fp32 non-FMA op/s (FMUL+FADD chains), out[1] FFMA op/s (1 per instr),
+ *   out[2] L2-resident read GB/s, out[3] HBM streaming read GB/s, out[4] SM clock MHz seen */
+int zrt_measure_peaks(int device, double *out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZRT_H */
