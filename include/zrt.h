@@ -110,7 +110,9 @@ typedef struct zrt_params {
     uint32_t sample_begin; /* global sample range [begin,end) traced by this call; 0,0 = all */
     uint32_t sample_end;   /*   (used to split samples-per-pixel across GPUs) */
     uint32_t flags;        /* ZRT_FLAG_* */
-    uint32_t reserved;
+    uint32_t sample_chunks;/* 0 = auto.  N > 0: split each pixel's samples over N device threads whose
+                              partial sums are added in chunk order; 1 keeps the reference's sequential
+                              f32 accumulation order raytrace.zig:177 */
 } zrt_params;
 
 enum {
@@ -177,9 +179,16 @@ int zrt_primary_hits(zrt_scene *scene, const zrt_camera *camera, const zrt_param
 
 /* Statistics of the flattened acceleration structure (0 nodes when the list path is used). */
 typedef struct zrt_bvh_info {
-    uint32_t nodes, leaves, max_depth, pruned_surfaces;
+    uint32_t nodes, leaves, max_depth; /* flattened tree that the device traverses */
+    uint32_t pruned_surfaces;          /* surfaces under a zero-thickness box: unreachable in the reference (Q4) */
+    uint32_t reference_nodes, reference_max_depth; /* the bvh.zig tree it was derived from */
 } zrt_bvh_info;
 int zrt_scene_bvh_info(zrt_scene *scene, uint32_t flags, zrt_bvh_info *out);
+
+/* Inspection hook for the parity tests: order[k] = surface id at left-first DFS position k of the
+ * reference tree (the tie-break key), visible[id] = 0 for pruned surfaces.  Both n_surfaces long.
+ * Works on a scene created with device = -1 (host only; such a scene cannot render). */
+int zrt_scene_bvh_order(zrt_scene *scene, uint32_t *order, uint8_t *visible);
 
 /* K0 microbenchmarks that measure the roofline denominators this path is judged against
  * (MEASURED_PEAKS.json has no FP32-issue or L2 number): results in out[0..n).

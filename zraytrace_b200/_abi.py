@@ -58,7 +58,7 @@ class Params(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("samples_per_pixel", C.c_uint32),
                 ("max_depth", C.c_uint32), ("bounded_volume_hierarchy", C.c_uint32), ("x_limit", C.c_uint32),
                 ("seed", C.c_uint64), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("sample_chunks", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -80,9 +80,11 @@ class Timing(C.Structure):
 
 class BvhInfo(C.Structure):
     _fields_ = [("nodes", C.c_uint32), ("leaves", C.c_uint32), ("max_depth", C.c_uint32),
-                ("pruned_surfaces", C.c_uint32)]
+                ("pruned_surfaces", C.c_uint32), ("reference_nodes", C.c_uint32),
+                ("reference_max_depth", C.c_uint32)]
 
 
 def make_params(width, height, spp, max_depth, bvh=True, x_limit=ZRT_XLIMIT_HEIGHT, seed=42,
-                sample_begin=0, sample_end=0, flags=0):
-    return Params(width, height, spp, max_depth, 1 if bvh else 0, x_limit, seed, sample_begin, sample_end, flags, 0)
+                sample_begin=0, sample_end=0, flags=0, sample_chunks=0):
+    return Params(width, height, spp, max_depth, 1 if bvh else 0, x_limit, seed, sample_begin, sample_end, flags,
+                  sample_chunks)

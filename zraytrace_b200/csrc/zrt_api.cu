@@ -1,0 +1,633 @@
+// zrt_api.cu — implementation of the C ABI declared in include/zrt.h.
+// Replaces raytrace.render() (raytrace.zig:136-203): validates and copies the caller's scene, flattens it
+// (list / BVH), keeps it resident in HBM, launches the sm_100a kernels and returns image + counters.
+// There is no CPU path in this file: without a device the compute entry points fail with
+// ZRT_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "zrt_internal.h"
+
+namespace zrt {
+void launch_trace(const KParams &P, int mode, cudaStream_t st);
+void launch_primary(const KParams &P, int mode, cudaStream_t st);
+void launch_resolve(const float *part, float *out, uint32_t n, uint32_t chunks, float scale, cudaStream_t st);
+void launch_peak_fp32(float *out, int blocks, int threads, int iters, cudaStream_t st);
+void launch_peak_ffma(float *out, int blocks, int threads, int iters, cudaStream_t st);
+void launch_peak_read(const float4 *src, size_t n4, int passes, float *out, int blocks, int threads, cudaStream_t st);
+} // namespace zrt
+
+using namespace zrt;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(ZRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t upload(const std::vector<T> &v) {
+        cudaError_t e = reserve(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    cudaError_t reserve(size_t count) {
+        if (count <= n) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+// one device-resident representation of the scene (list order, reference-tree order, or SAH tree)
+struct DevRep {
+    bool ready = false;
+    int mode = MODE_LIST;
+    DevBuf<DevSphere> spheres;
+    DevBuf<float4> triA, triE1, triE2;
+    DevBuf<TriMeta> triMeta;
+    DevBuf<uint32_t> list;
+    DevBuf<DevNode> nodes;
+    std::vector<DevSphere> h_spheres;
+    uint32_t n_spheres = 0, n_list = 0, root = REF_EMPTY;
+    FlatBvh info;
+    float prepare_ms = 0.0f;
+    void release() {
+        spheres.release(); triA.release(); triE1.release(); triE2.release();
+        triMeta.release(); list.release(); nodes.release();
+        ready = false;
+    }
+};
+
+} // namespace
+
+struct zrt_scene {
+    int device = -1;
+    HostScene host;
+    bool all_spheres = false;
+    DevBuf<DevMaterial> mats;
+    std::vector<uint8_t *> d_texels;
+    DevRep rep_list, rep_bvh, rep_sah;
+    FlatBvh host_bvh[2]; // host-only inspection (device == -1)
+    bool host_bvh_ready[2] = {false, false};
+    // scratch owned by the scene
+    DevBuf<float> part, image;
+    DevBuf<unsigned long long> counters;
+    DevBuf<uint32_t> hit_id;
+    DevBuf<float> hit_t;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+uint32_t packMaterial(const HostScene &hs, uint32_t m) {
+    const zrt_material &mat = hs.materials[m];
+    uint32_t w = (m & MAT_INDEX_MASK) | (mat.kind << MAT_KIND_SHIFT);
+    if (mat.kind != ZRT_MATERIAL_DIELECTRIC && hs.textures[mat.texture].kind == ZRT_TEXTURE_IMAGE) w |= MAT_IMAGE_BIT;
+    return w;
+}
+
+DevSphere makeSphere(const HostScene &hs, uint32_t surface, uint32_t slot) {
+    const zrt_sphere &s = hs.spheres[hs.surfaces[surface].index];
+    DevSphere d;
+    d.cx = s.center.x; d.cy = s.center.y; d.cz = s.center.z;
+    d.r2 = s.radius * s.radius;  // sphere.zig:34
+    d.inv_r = 1.0f / s.radius;   // sphere.zig:46
+    d.material = packMaterial(hs, s.material);
+    d.surface_id = surface;
+    d.slot = slot;
+    return d;
+}
+
+void makeTriangle(const HostScene &hs, uint32_t surface, float4 *A, float4 *E1, float4 *E2, TriMeta *meta) {
+    const zrt_triangle &t = hs.triangles[hs.surfaces[surface].index];
+    // triangle.zig:32-44: e1 = b - a, e2 = c - a, face_normal = e1 x e2 (vector.zig:70-74)
+    const float e1x = t.b.x - t.a.x, e1y = t.b.y - t.a.y, e1z = t.b.z - t.a.z;
+    const float e2x = t.c.x - t.a.x, e2y = t.c.y - t.a.y, e2z = t.c.z - t.a.z;
+    const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+    *A = float4{t.a.x, t.a.y, t.a.z, nx};
+    *E1 = float4{e1x, e1y, e1z, ny};
+    *E2 = float4{e2x, e2y, e2z, nz};
+    meta->material = packMaterial(hs, t.material);
+    meta->surface_id = surface;
+}
+
+int validate(const zrt_scene_desc *d) {
+    if (!d) return fail(ZRT_ERR_INVALID, "scene description is NULL");
+    if (d->n_surfaces && !d->surfaces) return fail(ZRT_ERR_INVALID, "surfaces is NULL");
+    if (d->n_spheres && !d->spheres) return fail(ZRT_ERR_INVALID, "spheres is NULL");
+    if (d->n_triangles && !d->triangles) return fail(ZRT_ERR_INVALID, "triangles is NULL");
+    if (d->n_materials && !d->materials) return fail(ZRT_ERR_INVALID, "materials is NULL");
+    if (d->n_textures && !d->textures) return fail(ZRT_ERR_INVALID, "textures is NULL");
+    if (d->n_surfaces > REF_INDEX_MASK || d->n_materials > MAT_INDEX_MASK) return fail(ZRT_ERR_INVALID, "scene too large");
+    for (uint32_t i = 0; i < d->n_surfaces; i++) {
+        const zrt_surface &s = d->surfaces[i];
+        if (s.kind == ZRT_SURFACE_SPHERE) {
+            if (s.index >= d->n_spheres) return fail(ZRT_ERR_INVALID, "surface refers to a missing sphere");
+            if (d->spheres[s.index].material >= d->n_materials) return fail(ZRT_ERR_INVALID, "sphere material out of range");
+        } else if (s.kind == ZRT_SURFACE_TRIANGLE) {
+            if (s.index >= d->n_triangles) return fail(ZRT_ERR_INVALID, "surface refers to a missing triangle");
+            if (d->triangles[s.index].material >= d->n_materials) return fail(ZRT_ERR_INVALID, "triangle material out of range");
+        } else {
+            return fail(ZRT_ERR_INVALID, "unknown surface kind");
+        }
+    }
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const zrt_material &m = d->materials[i];
+        if (m.kind > ZRT_MATERIAL_DIELECTRIC) return fail(ZRT_ERR_INVALID, "unknown material kind");
+        if (m.kind != ZRT_MATERIAL_DIELECTRIC && m.texture >= d->n_textures) return fail(ZRT_ERR_INVALID, "material texture out of range");
+    }
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const zrt_texture &t = d->textures[i];
+        if (t.kind == ZRT_TEXTURE_IMAGE) {
+            if (!t.pixels || t.width == 0 || t.height == 0 || (t.channels != 3 && t.channels != 4))
+                return fail(ZRT_ERR_INVALID, "image texture needs 8-bit RGB/RGBA pixels");
+        } else if (t.kind != ZRT_TEXTURE_COLOR) {
+            return fail(ZRT_ERR_INVALID, "unknown texture kind");
+        }
+    }
+    return ZRT_OK;
+}
+
+int uploadMaterials(zrt_scene *sc) {
+    const HostScene &hs = sc->host;
+    std::vector<DevMaterial> mats(hs.materials.size());
+    sc->d_texels.assign(hs.textures.size(), nullptr);
+    for (size_t i = 0; i < hs.textures.size(); i++) {
+        if (hs.textures[i].kind != ZRT_TEXTURE_IMAGE) continue;
+        const size_t bytes = hs.texels[i].size();
+        CUDA_TRY(cudaMalloc(&sc->d_texels[i], bytes));
+        CUDA_TRY(cudaMemcpy(sc->d_texels[i], hs.texels[i].data(), bytes, cudaMemcpyHostToDevice));
+    }
+    for (size_t i = 0; i < mats.size(); i++) {
+        const zrt_material &m = hs.materials[i];
+        DevMaterial d{};
+        d.kind = m.kind;
+        d.ior = m.index_of_refraction;
+        d.inv_ior = 1.0f / m.index_of_refraction; // material.zig:111
+        if (m.kind != ZRT_MATERIAL_DIELECTRIC) {
+            const zrt_texture &t = hs.textures[m.texture];
+            d.tex_kind = t.kind;
+            d.r = t.r; d.g = t.g; d.b = t.b;
+            d.u_off = t.u_offset; d.v_off = t.v_offset;
+            d.w = t.width; d.h = t.height; d.ch = t.channels;
+            d.pixels = sc->d_texels[m.texture];
+        }
+        mats[i] = d;
+    }
+    CUDA_TRY(sc->mats.upload(mats));
+    return ZRT_OK;
+}
+
+int buildListRep(zrt_scene *sc, DevRep &r) {
+    const HostScene &hs = sc->host;
+    const uint32_t n = (uint32_t)hs.surfaces.size();
+    std::vector<uint32_t> list(n);
+    std::vector<float4> A(n), E1(n), E2(n);
+    std::vector<TriMeta> meta(n);
+    r.h_spheres.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        if (hs.surfaces[i].kind == ZRT_SURFACE_SPHERE) {
+            list[i] = REF_LEAF | REF_SPHERE | (uint32_t)r.h_spheres.size();
+            r.h_spheres.push_back(makeSphere(hs, i, i));
+        } else {
+            list[i] = REF_LEAF | i; // triangle planes are indexed by list position
+            makeTriangle(hs, i, &A[i], &E1[i], &E2[i], &meta[i]);
+        }
+    }
+    r.n_spheres = (uint32_t)r.h_spheres.size();
+    r.n_list = n;
+    r.mode = (sc->all_spheres && n <= MAX_INLINE_SPHERES && n > 0) ? MODE_SPHERES : MODE_LIST;
+    CUDA_TRY(r.spheres.upload(r.h_spheres));
+    CUDA_TRY(r.list.upload(list));
+    if (hs.triangles.size()) {
+        CUDA_TRY(r.triA.upload(A)); CUDA_TRY(r.triE1.upload(E1)); CUDA_TRY(r.triE2.upload(E2));
+        CUDA_TRY(r.triMeta.upload(meta));
+    }
+    r.ready = true;
+    return ZRT_OK;
+}
+
+int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
+    const HostScene &hs = sc->host;
+    build_flat_bvh(hs, sah, &r.info);
+    if (r.info.max_depth + 2 >= (uint32_t)TRAVERSAL_STACK)
+        return fail(ZRT_ERR_INVALID, "BVH deeper than the traversal stack; retry with ZRT_FLAG_BVH_SAH");
+    const uint32_t slots = (uint32_t)r.info.slot_surface.size();
+    std::vector<float4> A(slots), E1(slots), E2(slots);
+    std::vector<TriMeta> meta(slots);
+    r.h_spheres.clear();
+    // sphere_seq in zrt_flatten.cpp numbers spheres in surface-list order
+    std::vector<uint32_t> slot_of(hs.surfaces.size(), 0);
+    for (uint32_t s = 0; s < slots; s++) slot_of[r.info.slot_surface[s]] = s;
+    for (uint32_t i = 0; i < hs.surfaces.size(); i++)
+        if (hs.surfaces[i].kind == ZRT_SURFACE_SPHERE) r.h_spheres.push_back(makeSphere(hs, i, slot_of[i]));
+    for (uint32_t s = 0; s < slots; s++) {
+        const uint32_t surf = r.info.slot_surface[s];
+        if (hs.surfaces[surf].kind == ZRT_SURFACE_TRIANGLE) makeTriangle(hs, surf, &A[s], &E1[s], &E2[s], &meta[s]);
+        else { A[s] = E1[s] = E2[s] = float4{0, 0, 0, 0}; meta[s] = TriMeta{0, surf}; }
+    }
+    r.n_spheres = (uint32_t)r.h_spheres.size();
+    r.n_list = 0;
+    r.root = r.info.root;
+    r.mode = MODE_BVH;
+    CUDA_TRY(r.spheres.upload(r.h_spheres));
+    CUDA_TRY(r.triA.upload(A)); CUDA_TRY(r.triE1.upload(E1)); CUDA_TRY(r.triE2.upload(E2));
+    CUDA_TRY(r.triMeta.upload(meta));
+    CUDA_TRY(r.nodes.upload(r.info.nodes));
+    r.ready = true;
+    return ZRT_OK;
+}
+
+// raytrace.zig:111-133 preprocessSufraces: BVH iff flag and more than 10 surfaces
+int selectRep(zrt_scene *sc, const zrt_params *p, DevRep **out) {
+    const bool use_bvh = p->bounded_volume_hierarchy != 0 && sc->host.surfaces.size() > 10;
+    DevRep *r = !use_bvh ? &sc->rep_list : ((p->flags & ZRT_FLAG_BVH_SAH) ? &sc->rep_sah : &sc->rep_bvh);
+    if (!r->ready) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = !use_bvh ? buildListRep(sc, *r) : buildBvhRep(sc, *r, r == &sc->rep_sah);
+        if (rc != ZRT_OK) return rc;
+        r->prepare_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    *out = r;
+    return ZRT_OK;
+}
+
+struct Plan {
+    KParams P;
+    int mode;
+    uint32_t n_samples;
+    size_t n_floats;
+};
+
+int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *r, Plan *plan) {
+    if (!cam || !p) return fail(ZRT_ERR_INVALID, "camera/params is NULL");
+    if (p->width == 0 || p->height == 0) return fail(ZRT_ERR_INVALID, "empty image");
+    if ((uint64_t)p->width * p->height > 0x7FFFFFFFull / 3) return fail(ZRT_ERR_INVALID, "image too large");
+    KParams &P = plan->P;
+    std::memset(&P, 0, sizeof(P));
+    P.ox = cam->origin.x; P.oy = cam->origin.y; P.oz = cam->origin.z;
+    P.llx = cam->lower_left_corner.x; P.lly = cam->lower_left_corner.y; P.llz = cam->lower_left_corner.z;
+    P.hx = cam->horizontal.x; P.hy = cam->horizontal.y; P.hz = cam->horizontal.z;
+    P.vx = cam->vertical.x; P.vy = cam->vertical.y; P.vz = cam->vertical.z;
+    P.width = p->width; P.height = p->height;
+    P.f_width = (float)p->width; P.f_height = (float)p->height; // raytrace.zig:153-154
+    // raytrace.zig:168 `while (x < image.height)`; when height > width the reference writes
+    // past the end of the row, which is clamped here
+    P.x_end = (p->x_limit == ZRT_XLIMIT_WIDTH) ? p->width : (p->height < p->width ? p->height : p->width);
+    uint32_t sb = p->sample_begin, se = p->sample_end;
+    if (sb == 0 && se == 0) se = p->samples_per_pixel;
+    if (se < sb || se > p->samples_per_pixel) return fail(ZRT_ERR_INVALID, "bad sample range");
+    P.s_begin = sb; P.s_end = se;
+    plan->n_samples = se - sb;
+    const uint64_t pixels = (uint64_t)P.x_end * P.height;
+    uint32_t chunks = p->sample_chunks;
+    if (chunks == 0) { // enough threads for ~4 waves of 148 SMs x 1024 resident threads
+        const uint64_t target = 600000;
+        chunks = (uint32_t)((target + pixels - 1) / pixels);
+    }
+    if (chunks > plan->n_samples) chunks = plan->n_samples;
+    if (chunks < 1) chunks = 1;
+    P.chunk_len = (plan->n_samples + chunks - 1) / chunks;
+    if (P.chunk_len == 0) P.chunk_len = 1;
+    P.chunks = plan->n_samples ? (plan->n_samples + P.chunk_len - 1) / P.chunk_len : 1;
+    P.max_depth = p->max_depth;
+    P.seed32 = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
+    P.color_scale = (p->flags & ZRT_FLAG_RAW_SUM) ? 1.0f : 1.0f / (float)p->samples_per_pixel; // raytrace.zig:157
+    P.count_pixels = (sb == 0) ? 1u : 0u;
+    P.n_spheres = r->n_spheres; P.n_list = r->n_list; P.root = r->root;
+    P.spheres = r->spheres.p;
+    P.triA = r->triA.p; P.triE1 = r->triE1.p; P.triE2 = r->triE2.p; P.triMeta = r->triMeta.p;
+    P.list = r->list.p; P.nodes = r->nodes.p; P.mats = sc->mats.p;
+    if (r->mode == MODE_SPHERES)
+        for (uint32_t i = 0; i < r->n_spheres; i++) P.inl[i] = r->h_spheres[i];
+    plan->mode = r->mode;
+    plan->n_floats = (size_t)p->width * p->height * 3;
+    return ZRT_OK;
+}
+
+// enqueue everything for one render on `st`; d_rgb receives the final image
+int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d_counters, cudaStream_t st,
+                  cudaEvent_t e_k0, cudaEvent_t e_k1, cudaEvent_t e_r1, uint32_t *launches) {
+    KParams &P = plan.P;
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, 6 * sizeof(unsigned long long), st));
+    float *trace_out = d_rgb;
+    if (P.chunks > 1) {
+        CUDA_TRY(sc->part.reserve(plan.n_floats * P.chunks));
+        trace_out = sc->part.p;
+    }
+    // pixels the reference never writes (x >= height, Q1) stay black: image.zig:80-90
+    if (P.x_end < P.width || P.chunks > 1) CUDA_TRY(cudaMemsetAsync(trace_out, 0, plan.n_floats * P.chunks * sizeof(float), st));
+    P.out = trace_out;
+    P.counters = d_counters;
+    *launches = 0;
+    if (e_k0) CUDA_TRY(cudaEventRecord(e_k0, st));
+    if (plan.n_samples > 0) {
+        launch_trace(P, plan.mode, st);
+        (*launches)++;
+    } else {
+        CUDA_TRY(cudaMemsetAsync(d_rgb, 0, plan.n_floats * sizeof(float), st));
+    }
+    if (e_k1) CUDA_TRY(cudaEventRecord(e_k1, st));
+    if (P.chunks > 1) {
+        launch_resolve(sc->part.p, d_rgb, (uint32_t)plan.n_floats, P.chunks, P.color_scale, st);
+        (*launches)++;
+    }
+    if (e_r1) CUDA_TRY(cudaEventRecord(e_r1, st));
+    CUDA_TRY(cudaGetLastError());
+    return ZRT_OK;
+}
+
+int requireDevice(zrt_scene *sc) {
+    if (!sc) return fail(ZRT_ERR_INVALID, "scene is NULL");
+    if (sc->device < 0) return fail(ZRT_ERR_NO_DEVICE, "scene was created without a device; libzrt has no CPU path");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    return ZRT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int zrt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *zrt_last_error(void) { return g_error.c_str(); }
+
+int zrt_scene_create(const zrt_scene_desc *desc, int device, zrt_scene **out) {
+    if (!out) return fail(ZRT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = validate(desc);
+    if (rc != ZRT_OK) return rc;
+    if (device >= 0) {
+        const int n = zrt_device_count();
+        if (n == 0) return fail(ZRT_ERR_NO_DEVICE, "no CUDA device visible; libzrt has no CPU path");
+        if (device >= n) return fail(ZRT_ERR_INVALID, "device index out of range");
+    }
+    zrt_scene *sc = new (std::nothrow) zrt_scene();
+    if (!sc) return fail(ZRT_ERR_OOM, "out of memory");
+    try {
+        HostScene &hs = sc->host;
+        hs.surfaces.assign(desc->surfaces, desc->surfaces + desc->n_surfaces);
+        hs.spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
+        hs.triangles.assign(desc->triangles, desc->triangles + desc->n_triangles);
+        hs.materials.assign(desc->materials, desc->materials + desc->n_materials);
+        hs.textures.assign(desc->textures, desc->textures + desc->n_textures);
+        hs.texels.resize(desc->n_textures);
+        for (uint32_t i = 0; i < desc->n_textures; i++) {
+            zrt_texture &t = hs.textures[i];
+            if (t.kind != ZRT_TEXTURE_IMAGE) continue;
+            const size_t bytes = (size_t)t.width * t.height * t.channels;
+            hs.texels[i].assign(t.pixels, t.pixels + bytes);
+            t.pixels = hs.texels[i].data();
+        }
+    } catch (const std::bad_alloc &) {
+        delete sc;
+        return fail(ZRT_ERR_OOM, "out of memory");
+    }
+    sc->all_spheres = true;
+    for (const auto &s : sc->host.surfaces) sc->all_spheres &= (s.kind == ZRT_SURFACE_SPHERE);
+    sc->device = device;
+    if (device >= 0) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&sc->ev[i]);
+        if (e != cudaSuccess) {
+            const std::string msg = cudaGetErrorString(e);
+            zrt_scene_destroy(sc);
+            return fail(ZRT_ERR_CUDA, "device setup failed: " + msg);
+        }
+        rc = uploadMaterials(sc);
+        if (rc != ZRT_OK) {
+            zrt_scene_destroy(sc);
+            return rc;
+        }
+    }
+    *out = sc;
+    return ZRT_OK;
+}
+
+void zrt_scene_destroy(zrt_scene *sc) {
+    if (!sc) return;
+    if (sc->device >= 0) {
+        cudaSetDevice(sc->device);
+        if (sc->stream) cudaStreamSynchronize(sc->stream);
+        sc->rep_list.release(); sc->rep_bvh.release(); sc->rep_sah.release();
+        sc->mats.release(); sc->part.release(); sc->image.release(); sc->counters.release();
+        sc->hit_id.release(); sc->hit_t.release();
+        for (uint8_t *p : sc->d_texels)
+            if (p) cudaFree(p);
+        for (auto &e : sc->ev)
+            if (e) cudaEventDestroy(e);
+        if (sc->stream) cudaStreamDestroy(sc->stream);
+    }
+    delete sc;
+}
+
+int zrt_render(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, float *out_rgb,
+               zrt_counters *counters, zrt_timing *timing) {
+    int rc = requireDevice(sc);
+    if (rc != ZRT_OK) return rc;
+    if (!out_rgb) return fail(ZRT_ERR_INVALID, "out_rgb is NULL");
+    if (!params) return fail(ZRT_ERR_INVALID, "params is NULL");
+    DevRep *rep = nullptr;
+    const auto t_prep0 = std::chrono::steady_clock::now();
+    rc = selectRep(sc, params, &rep);
+    if (rc != ZRT_OK) return rc;
+    const float prep_now = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_prep0).count();
+    Plan plan;
+    rc = makePlan(sc, camera, params, rep, &plan);
+    if (rc != ZRT_OK) return rc;
+    CUDA_TRY(sc->image.reserve(plan.n_floats));
+    CUDA_TRY(sc->counters.reserve(6));
+    uint32_t launches = 0;
+    rc = enqueueRender(sc, plan, sc->image.p, sc->counters.p, sc->stream, sc->ev[0], sc->ev[1], sc->ev[2], &launches);
+    if (rc != ZRT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, sc->image.p, plan.n_floats * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    unsigned long long h_counters[6];
+    CUDA_TRY(cudaMemcpyAsync(h_counters, sc->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaEventRecord(sc->ev[3], sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    if (counters) {
+        counters->recursion_depth_hits = h_counters[0];
+        counters->reflections = h_counters[1];
+        counters->background_hits = h_counters[2];
+        counters->pixels_processed = h_counters[3];
+        counters->samples_processed = h_counters[4];
+        counters->rays_processed = h_counters[5];
+    }
+    if (timing) {
+        float k = 0, r = 0, tot = 0;
+        cudaEventElapsedTime(&k, sc->ev[0], sc->ev[1]);
+        cudaEventElapsedTime(&r, sc->ev[1], sc->ev[2]);
+        cudaEventElapsedTime(&tot, sc->ev[0], sc->ev[3]);
+        timing->prepare_ms = prep_now;
+        timing->kernel_ms = k;
+        timing->resolve_ms = r;
+        timing->total_ms = tot;
+        timing->launches = launches;
+        timing->bvh_nodes = (uint32_t)rep->info.nodes.size();
+    }
+    return ZRT_OK;
+}
+
+int zrt_render_device(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, float *d_rgb,
+                      uint64_t *d_counters, void *stream) {
+    int rc = requireDevice(sc);
+    if (rc != ZRT_OK) return rc;
+    if (!d_rgb || !d_counters) return fail(ZRT_ERR_INVALID, "device output pointers are NULL");
+    if (!params) return fail(ZRT_ERR_INVALID, "params is NULL");
+    DevRep *rep = nullptr;
+    rc = selectRep(sc, params, &rep);
+    if (rc != ZRT_OK) return rc;
+    Plan plan;
+    rc = makePlan(sc, camera, params, rep, &plan);
+    if (rc != ZRT_OK) return rc;
+    uint32_t launches = 0;
+    return enqueueRender(sc, plan, d_rgb, reinterpret_cast<unsigned long long *>(d_counters),
+                         static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, &launches);
+}
+
+int zrt_primary_hits(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, int jitter,
+                     uint32_t *surface_id, float *t) {
+    int rc = requireDevice(sc);
+    if (rc != ZRT_OK) return rc;
+    if (!surface_id || !t) return fail(ZRT_ERR_INVALID, "output pointers are NULL");
+    if (!params) return fail(ZRT_ERR_INVALID, "params is NULL");
+    DevRep *rep = nullptr;
+    rc = selectRep(sc, params, &rep);
+    if (rc != ZRT_OK) return rc;
+    Plan plan;
+    zrt_params p2 = *params;
+    if (p2.samples_per_pixel == 0) p2.samples_per_pixel = 1;
+    if (p2.sample_begin == 0 && p2.sample_end == 0) p2.sample_end = p2.samples_per_pixel;
+    rc = makePlan(sc, camera, &p2, rep, &plan);
+    if (rc != ZRT_OK) return rc;
+    const size_t n = (size_t)params->width * params->height;
+    CUDA_TRY(sc->hit_id.reserve(n));
+    CUDA_TRY(sc->hit_t.reserve(n));
+    plan.P.hit_id = sc->hit_id.p;
+    plan.P.hit_t = sc->hit_t.p;
+    plan.P.jitter = jitter ? 1u : 0u;
+    launch_primary(plan.P, plan.mode, sc->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(surface_id, sc->hit_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaMemcpyAsync(t, sc->hit_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    return ZRT_OK;
+}
+
+static const FlatBvh *hostBvh(zrt_scene *sc, uint32_t flags) {
+    const int k = (flags & ZRT_FLAG_BVH_SAH) ? 1 : 0;
+    DevRep &r = k ? sc->rep_sah : sc->rep_bvh;
+    if (r.ready) return &r.info;
+    if (!sc->host_bvh_ready[k]) {
+        build_flat_bvh(sc->host, k != 0, &sc->host_bvh[k]);
+        sc->host_bvh_ready[k] = true;
+    }
+    return &sc->host_bvh[k];
+}
+
+int zrt_scene_bvh_info(zrt_scene *sc, uint32_t flags, zrt_bvh_info *out) {
+    if (!sc || !out) return fail(ZRT_ERR_INVALID, "NULL argument");
+    const FlatBvh *b = hostBvh(sc, flags);
+    out->nodes = (uint32_t)b->nodes.size();
+    out->leaves = b->leaves;
+    out->max_depth = b->max_depth;
+    out->pruned_surfaces = b->pruned;
+    out->reference_nodes = b->ref_nodes;
+    out->reference_max_depth = b->ref_max_depth;
+    return ZRT_OK;
+}
+
+int zrt_scene_bvh_order(zrt_scene *sc, uint32_t *order, uint8_t *visible) {
+    if (!sc || !order || !visible) return fail(ZRT_ERR_INVALID, "NULL argument");
+    const FlatBvh *b = hostBvh(sc, 0);
+    for (size_t s = 0; s < b->slot_surface.size(); s++) order[s] = b->slot_surface[s];
+    std::memset(visible, 0, sc->host.surfaces.size());
+    for (size_t s = 0; s < b->slot_surface.size(); s++) visible[b->slot_surface[s]] = b->slot_visible[s];
+    return ZRT_OK;
+}
+
+int zrt_measure_peaks(int device, double *out, int n) {
+    if (!out || n < 5) return fail(ZRT_ERR_INVALID, "need room for 5 results");
+    if (zrt_device_count() == 0) return fail(ZRT_ERR_NO_DEVICE, "no CUDA device visible");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float *d_out = nullptr;
+    const int blocks = sms * 8, threads = 256, iters = 8192;
+    CUDA_TRY(cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(float)));
+    auto best_of = [&](auto &&launch, int reps, float *best_ms) -> cudaError_t {
+        *best_ms = 1e30f;
+        for (int i = 0; i < reps + 2; i++) {
+            cudaEventRecord(e0, 0);
+            launch();
+            cudaEventRecord(e1, 0);
+            cudaError_t e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess) return e;
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (i >= 2 && ms < *best_ms) *best_ms = ms;
+        }
+        return cudaGetLastError();
+    };
+    float ms;
+    CUDA_TRY(best_of([&] { launch_peak_fp32(d_out, blocks, threads, iters, 0); }, 5, &ms));
+    out[0] = (double)blocks * threads * iters * 16.0 / (ms * 1e-3);
+    CUDA_TRY(best_of([&] { launch_peak_ffma(d_out, blocks, threads, iters, 0); }, 5, &ms));
+    out[1] = (double)blocks * threads * iters * 16.0 / (ms * 1e-3);
+    // L2-resident read: 32 MiB buffer read 16 times per launch
+    float4 *buf = nullptr;
+    const size_t l2_bytes = 32ull << 20, hbm_bytes = 1ull << 30;
+    CUDA_TRY(cudaMalloc(&buf, hbm_bytes));
+    CUDA_TRY(cudaMemset(buf, 0, hbm_bytes));
+    CUDA_TRY(best_of([&] { launch_peak_read(buf, l2_bytes / 16, 16, d_out, sms * 8, 512, 0); }, 5, &ms));
+    out[2] = (double)l2_bytes * 16 / (ms * 1e-3) / 1e9;
+    CUDA_TRY(best_of([&] { launch_peak_read(buf, hbm_bytes / 16, 1, d_out, sms * 8, 512, 0); }, 5, &ms));
+    out[3] = (double)hbm_bytes / (ms * 1e-3) / 1e9;
+    out[4] = prop.clockRate / 1000.0;
+    cudaFree(buf);
+    cudaFree(d_out);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ZRT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,139 @@
+// zrt_internal.h — flattened scene layout shared by the host flattener and the sm_100a kernels.
+// Everything here is resident in HBM (in practice L1/L2: a scene is at most a few MB).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/zrt.h"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+#endif
+
+namespace zrt {
+
+// ---- primitive references (BVH child refs and list entries) -------------------------------------
+// ref >= 0            : inner node index
+// ref & 0x80000000    : leaf; bit 30 = sphere, low 30 bits = triangle slot / sphere index
+constexpr uint32_t REF_LEAF = 0x80000000u;
+constexpr uint32_t REF_SPHERE = 0x40000000u;
+constexpr uint32_t REF_INDEX_MASK = 0x3FFFFFFFu;
+constexpr uint32_t REF_EMPTY = 0x7FFFFFFFu; // child slot removed by flat-box pruning
+
+// Material word carried by every primitive: the kind and "samples an image" bit ride along with the
+// index so that shading can branch without first fetching the material record.
+constexpr uint32_t MAT_INDEX_MASK = 0x00FFFFFFu;
+constexpr uint32_t MAT_KIND_SHIFT = 24;           // 2 bits: ZRT_MATERIAL_*
+constexpr uint32_t MAT_IMAGE_BIT = 1u << 26;      // lambertian/metal whose texture is an image
+
+// sphere.zig:15-20, 32 B = two 128-bit loads.  r2 and inv_r are the f32 values the reference
+// recomputes on every test (`radius * radius` sphere.zig:34, `1.0/radius` sphere.zig:46): computing
+// them once on the host with the same IEEE operation is bit-identical.
+struct alignas(16) DevSphere {
+    float cx, cy, cz, r2;
+    float inv_r;
+    uint32_t material;   // packed material word
+    uint32_t surface_id; // index in the caller's surface list
+    uint32_t slot;       // tie-break key: left-first DFS position in the reference tree / list position
+};
+static_assert(sizeof(DevSphere) == 32, "DevSphere layout");
+
+// Triangles: structure of three float4 planes (16-byte SoA), indexed by slot:
+//   triA [i] = (a.x,  a.y,  a.z,  n.x)     triangle.zig:15-30 fields a, e1, e2, face_normal
+//   triE1[i] = (e1.x, e1.y, e1.z, n.y)     (face_unit_normal is recomputed for the one final hit)
+//   triE2[i] = (e2.x, e2.y, e2.z, n.z)
+// plus triMeta[i] = (packed material word, surface_id).  48 B read per test as three LDG.128.
+struct alignas(8) TriMeta {
+    uint32_t material, surface_id;
+};
+
+// Materials with their texture folded in (material.zig:16-29 + texture.zig:7-16), 64 B.
+struct alignas(16) DevMaterial {
+    uint32_t kind;     // ZRT_MATERIAL_*
+    uint32_t tex_kind; // ZRT_TEXTURE_*
+    float ior;         // index_of_refraction
+    float inv_ior;     // 1.0f / ior (material.zig:111)
+    float r, g, b;     // ColorTexture.color
+    float u_off;
+    float v_off;
+    uint32_t w, h, ch;
+    const uint8_t *pixels; // device pointer, rows bottom-up
+    uint64_t pad;
+};
+static_assert(sizeof(DevMaterial) == 64, "DevMaterial layout");
+
+// 64-byte BVH node, cache-line-half aligned, read as four 128-bit loads.
+//   q0 = (lmin.x, lmin.y, lmin.z, lmax.x)
+//   q1 = (lmax.y, lmax.z, rmin.x, rmin.y)
+//   q2 = (rmin.z, rmax.x, rmax.y, rmax.z)
+//   q3 = (left_ref, right_ref, -, -)
+struct alignas(64) DevNode {
+    float lmin[3], lmax[3], rmin[3], rmax[3];
+    uint32_t left, right, pad0, pad1;
+};
+static_assert(sizeof(DevNode) == 64, "DevNode layout");
+
+constexpr int MAX_INLINE_SPHERES = 8;
+constexpr int TRAVERSAL_STACK = 64;
+
+// Everything a kernel needs, passed by value as a __grid_constant__ parameter (constant bank).
+struct KParams {
+    // camera.zig:11-15
+    float ox, oy, oz, llx, lly, llz, hx, hy, hz, vx, vy, vz;
+    float f_width, f_height;
+    uint32_t width, height, x_end;
+    uint32_t s_begin, s_end; // global sample range of this launch
+    uint32_t chunks, chunk_len; // samples split over `chunks` threads per pixel
+    uint32_t max_depth, seed32;
+    float color_scale; // 1/spp, or 1 for ZRT_FLAG_RAW_SUM
+    uint32_t count_pixels; // 1 if this launch owns sample 0 (pixels_processed is counted once)
+    uint32_t jitter;       // primary-hit kernel only
+    // scene
+    uint32_t n_spheres, n_list;
+    uint32_t root; // BVH root ref
+    const DevSphere *spheres;
+    const float4 *triA, *triE1, *triE2;
+    const TriMeta *triMeta;
+    const uint32_t *list; // list mode: refs in caller order
+    const DevNode *nodes;
+    const DevMaterial *mats;
+    // outputs
+    float *out;                   // [chunks][height][width][3]
+    unsigned long long *counters; // 6 x u64, zrt_counters order
+    uint32_t *hit_id;             // primary-hit kernel
+    float *hit_t;
+    DevSphere inl[MAX_INLINE_SPHERES]; // spheres-only scenes: operands straight from the constant bank
+};
+
+enum TraceMode { MODE_SPHERES = 0, MODE_LIST = 1, MODE_BVH = 2 };
+
+// ---- host-side flattened scene (zrt_flatten.cpp) ------------------------------------------------
+struct FlatBvh {
+    std::vector<DevNode> nodes;
+    uint32_t root = REF_EMPTY;
+    std::vector<uint32_t> slot_surface;  // slot -> surface id (DFS order of the reference tree)
+    std::vector<uint8_t> slot_visible;   // 0 if pruned (under a zero-thickness box)
+    uint32_t ref_nodes = 0, ref_max_depth = 0, leaves = 0, pruned = 0, max_depth = 0;
+};
+
+struct HostScene {
+    zrt_scene_desc desc{}; // pointers into the vectors below
+    std::vector<zrt_surface> surfaces;
+    std::vector<zrt_sphere> spheres;
+    std::vector<zrt_triangle> triangles;
+    std::vector<zrt_material> materials;
+    std::vector<zrt_texture> textures;
+    std::vector<std::vector<uint8_t>> texels;
+};
+
+// Faithful rebuild of the reference tree (bvh.zig:62-185) followed by flattening and flat-box
+// pruning.  sah = true additionally re-splits the surviving primitives with a binned SAH builder;
+// slots (tie-break keys) always come from the reference tree.
+void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out);
+
+} // namespace zrt

@@ -1,0 +1,117 @@
+"""ctypes binding of libzrt.so (include/zrt.h).  This is the host-side mirror of the reference's
+`raytrace.render(allocator, random, camera, surfaces, render_params)` (raytrace.zig:136-138): same
+arguments in, image + Progress counters out.  There is no CPU fallback anywhere in this package: if the
+CUDA library is missing or no device is visible, calls raise."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzrt.so")
+_lib = None
+
+
+class ZrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libzrt error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libzrt.so (built in-tree by __graft_entry__.build() / make -C zraytrace_b200/csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZrtError(A.ZRT_ERR_NO_DEVICE, f"{LIB_PATH} is not built; run __graft_entry__.build() "
+                                                "(there is no Python/CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        P = C.POINTER
+        L.zrt_device_count.restype = C.c_int
+        L.zrt_last_error.restype = C.c_char_p
+        L.zrt_scene_create.argtypes = [P(A.SceneDesc), C.c_int, P(C.c_void_p)]
+        L.zrt_scene_destroy.argtypes = [C.c_void_p]
+        L.zrt_scene_destroy.restype = None
+        L.zrt_render.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_void_p, P(A.Counters), P(A.Timing)]
+        L.zrt_render_device.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zrt_primary_hits.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_int, C.c_void_p, C.c_void_p]
+        L.zrt_scene_bvh_info.argtypes = [C.c_void_p, C.c_uint32, P(A.BvhInfo)]
+        L.zrt_scene_bvh_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zrt_measure_peaks.argtypes = [C.c_int, P(C.c_double), C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise ZrtError(rc, lib().zrt_last_error().decode())
+
+
+def device_count():
+    return lib().zrt_device_count()
+
+
+class Scene:
+    """Device-resident flattened scene (`zrt_scene*`).  device=-1 keeps it on the host (inspection only)."""
+
+    def __init__(self, built_scene_or_desc, device=0):
+        desc = getattr(built_scene_or_desc, "desc", built_scene_or_desc)
+        self.n_surfaces = desc.n_surfaces
+        self.device = device
+        self._h = C.c_void_p()
+        _check(lib().zrt_scene_create(C.byref(desc), device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().zrt_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def render(self, camera, params):
+        """-> (image float32 [H][W][3] row 0 = bottom, Counters, Timing)   (raytrace.zig:136-203)"""
+        img = np.empty((params.height, params.width, 3), np.float32)
+        cnt, tm = A.Counters(), A.Timing()
+        _check(lib().zrt_render(self._h, C.byref(camera), C.byref(params), img.ctypes.data, C.byref(cnt), C.byref(tm)))
+        return img, cnt, tm
+
+    def render_device(self, camera, params, d_rgb_ptr, d_counters_ptr, stream_ptr=0):
+        """Asynchronous render into device memory (raw pointers, e.g. torch tensor .data_ptr())."""
+        _check(lib().zrt_render_device(self._h, C.byref(camera), C.byref(params), C.c_void_p(d_rgb_ptr),
+                                       C.c_void_p(d_counters_ptr), C.c_void_p(stream_ptr)))
+
+    def primary_hits(self, camera, params, jitter=0):
+        ids = np.empty((params.height, params.width), np.uint32)
+        t = np.empty((params.height, params.width), np.float32)
+        _check(lib().zrt_primary_hits(self._h, C.byref(camera), C.byref(params), jitter, ids.ctypes.data, t.ctypes.data))
+        return ids, t
+
+    def bvh_info(self, flags=0):
+        info = A.BvhInfo()
+        _check(lib().zrt_scene_bvh_info(self._h, flags, C.byref(info)))
+        return info
+
+    def bvh_order(self):
+        order = np.zeros(self.n_surfaces, np.uint32)
+        vis = np.zeros(self.n_surfaces, np.uint8)
+        _check(lib().zrt_scene_bvh_order(self._h, order.ctypes.data, vis.ctypes.data))
+        return order, vis.astype(bool)
+
+
+def measure_peaks(device=0):
+    out = (C.c_double * 5)()
+    _check(lib().zrt_measure_peaks(device, out, 5))
+    return {"fp32_nofma_ops": out[0], "ffma_instr": out[1], "l2_read_gbs": out[2], "hbm_read_gbs": out[3],
+            "sm_max_mhz": out[4]}
