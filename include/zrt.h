@@ -169,6 +169,10 @@ int zrt_render(zrt_scene *scene, const zrt_camera *camera, const zrt_params *par
 int zrt_render_device(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
                       float *d_rgb, uint64_t *d_counters, void *stream);
 
+/* Number of libzrt kernels launched on behalf of this scene since it was created (trace, resolve and
+ * primary-hit kernels; driver memsets and copies are not counted). */
+uint64_t zrt_scene_launch_count(const zrt_scene *scene);
+
 /* Parity AOV: first iteration of rayColor (raytrace.zig:71-81) for every pixel.  surface_id[y*w+x] is
  * the index in desc.surfaces of the closest hit (0xFFFFFFFF = background), t its ray parameter.
  * jitter = 0 traces (u,v) = ((x-0.5)/w,(y-0.5)/h), i.e. raytrace.zig:173-174 with xi = 0;

@@ -1,0 +1,160 @@
+"""CPU tests of the C++ host mirror (scenes / camera / OBJ / PNG) against independent Python restatements,
+and of the C-ABI surface: the library loads, exports every symbol the headers declare, and refuses to
+compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import zro_py
+from tests import scenes_py
+from zraytrace_b200 import _abi as A
+from zraytrace_b200 import host
+from zraytrace_b200 import lib as Z
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = Z.lib()
+    declared = set()
+    for h in ("zrt.h", "zrt_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(zrt_[a-z0-9_]+)\s*\(", src))
+    assert len(declared) >= 18
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libzrt.so does not export {name}"
+
+
+def test_abi_struct_sizes_match_header():
+    # sizes computed from include/zrt.h by a C compiler would be: see zrt.h; keep ctypes in sync
+    assert C.sizeof(A.Sphere) == 20 and C.sizeof(A.Triangle) == 40 and C.sizeof(A.Surface) == 8
+    assert C.sizeof(A.Material) == 12 and C.sizeof(A.Texture) == 48 and C.sizeof(A.Camera) == 48
+    assert C.sizeof(A.Params) == 48 and C.sizeof(A.Counters) == 48 and C.sizeof(A.SceneDesc) == 80
+
+
+def test_no_cpu_fallback_without_device():
+    if Z.device_count() > 0:
+        pytest.skip("a device is visible")
+    sc, cam = scenes_py.three_balls()
+    with pytest.raises(Z.ZrtError) as e:
+        Z.Scene(sc, device=0)
+    assert e.value.code == A.ZRT_ERR_NO_DEVICE
+    with Z.Scene(sc, device=-1) as hs:
+        with pytest.raises(Z.ZrtError) as e:
+            hs.render(cam, A.make_params(8, 8, 1, 2))
+        assert e.value.code == A.ZRT_ERR_NO_DEVICE
+
+
+def test_invalid_scene_rejected():
+    from zraytrace_b200.scene import SceneBuilder
+    b = SceneBuilder()
+    b.sphere((0, 0, 0), 1.0, 3)  # material index out of range
+    with pytest.raises(Z.ZrtError) as e:
+        Z.Scene(b.build(), device=-1)
+    assert e.value.code == A.ZRT_ERR_INVALID
+
+
+def test_camera_init_matches_oracle():  # camera.zig:17-35
+    for args in (((0, 0, -7), (0, 0, 1), (0, 1, 0), 45.0, 1.0), ((1, 0, 0), (0, 0, 1), (0, 1, 0), 45.0, 1.0),
+                 ((-8, 0, -10), (0, 0, 1), (0, 1, 0), 45.0, 16 / 9)):
+        a, b = host.camera_init(*args), zro_py.camera_init(*args)
+        assert bytes(a) == bytes(b)
+    assert host.camera_init((1, 0, 0), (0, 0, 1), (0, 1, 0), 45.0, 1.0).origin.tuple() == (1.0, 0.0, 0.0)  # camera.zig:58-66
+
+
+@pytest.mark.parametrize("name", ["Man", "bunny", "teapot"])
+def test_obj_reader_matches_python_parser(name):  # obj_reader.zig:201-226
+    got = host.read_obj(os.path.join(host.ASSETS, "models", name + ".obj.gz"))
+    want = scenes_py.read_obj(name)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert len(got) == {"Man": 3933, "bunny": 4968, "teapot": 6320}[name]
+
+
+@pytest.mark.parametrize("name", ["earthmap.png", "nitor-logo-25.png"])
+def test_png_reader_matches_pil(name):  # png_image.zig:19-94 incl. the row flip
+    got = host.png_read(os.path.join(host.ASSETS, "images", name))
+    want = scenes_py.read_png_bottom_up(name)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_png_writer_quantisation_and_flip(tmp_path):  # png_image.zig:96-148
+    rng = np.random.default_rng(3)
+    img = rng.random((7, 5, 3)).astype(np.float32) * 1.2 - 0.1
+    path = str(tmp_path / "o.png")
+    host.png_write(path, img)
+    back = np.array(Image.open(path))
+    want = np.array([[[zro_py.lib().zro_quantize(float(c)) for c in px] for px in row] for row in img], np.uint8)[::-1]
+    assert back.shape == (7, 5, 3) and np.array_equal(back, want)
+    assert np.array_equal(host.png_read(path)[..., :3], want[::-1])
+
+
+def _desc_arrays(d):
+    def arr(ptr, n, ctype_size):
+        return bytes(C.string_at(ptr, n * ctype_size)) if n else b""
+    tex = []
+    for i in range(d.n_textures):
+        t = d.textures[i]
+        px = bytes(C.string_at(t.pixels, t.width * t.height * t.channels)) if t.kind == A.ZRT_TEXTURE_IMAGE else b""
+        tex.append((t.kind, t.r, t.g, t.b, t.width, t.height, t.channels, t.u_offset, t.v_offset, px))
+    return (arr(d.surfaces, d.n_surfaces, 8), arr(d.spheres, d.n_spheres, 20), arr(d.triangles, d.n_triangles, 40),
+            arr(d.materials, d.n_materials, 12), tex)
+
+
+@pytest.mark.parametrize("index,variant,py", [
+    (host.SCENE_MAN, 0, scenes_py.man_and_ball), (host.SCENE_THREE_BALLS, 0, scenes_py.three_balls),
+    (host.SCENE_BUNNY, 0, scenes_py.bunny_and_ball),
+    (host.SCENE_BUNNY, host.VARIANT_BUNNY_GLASS, lambda: scenes_py.bunny_and_ball(dielectric=True)),
+    (host.SCENE_TEAPOT, 0, scenes_py.teapot_and_ball), (host.SCENE_TEAPOT_CIRCLE, 0, scenes_py.teapot_and_ball_circle)])
+def test_scene_builders_match_python_restatement(index, variant, py):  # scenes.zig:26-260
+    hs = host.HostScene(index, variant=variant)
+    sc, cam = py()
+    assert bytes(hs.camera) == bytes(cam)
+    a, b = _desc_arrays(hs.desc), _desc_arrays(sc.desc)
+    # surfaces, spheres and triangles are identical; material/texture tables may be ordered differently, so
+    # compare what every surface resolves to
+    assert a[0] == b[0] and hs.desc.n_spheres == sc.desc.n_spheres and hs.desc.n_triangles == sc.desc.n_triangles
+
+    def resolved(d, tex, kind, i):
+        m = d.materials[(d.spheres[i] if kind == 0 else d.triangles[i]).material]
+        return (m.kind, m.index_of_refraction if m.kind == 2 else 0.0, tex[m.texture] if m.kind != 2 else None)
+    for kind, n in ((0, sc.desc.n_spheres), (1, min(sc.desc.n_triangles, 50))):
+        for i in range(n):
+            assert resolved(hs.desc, a[4], kind, i) == resolved(sc.desc, b[4], kind, i)
+    g = lambda d, i: bytes(d.spheres[i])[:16]
+    assert all(g(hs.desc, i) == g(sc.desc, i) for i in range(sc.desc.n_spheres))
+    t = lambda d, i: bytes(d.triangles[i])[:36]
+    assert all(t(hs.desc, i) == t(sc.desc, i) for i in range(sc.desc.n_triangles))
+    hs.close()
+
+
+def test_goat_scene_reports_missing_model_and_substitute_builds():
+    with pytest.raises(Z.ZrtError) as e:  # models/high_poly_goat.obj is absent from the reference checkout
+        host.HostScene(host.SCENE_GOAT)
+    assert e.value.code == A.ZRT_ERR_IO
+    hs = host.HostScene(host.SCENE_GOAT, variant=host.VARIANT_GOAT_SUBSTITUTE, aspect_ratio=16 / 9)
+    assert hs.desc.n_triangles == 3933 + 4968 * 64 and hs.desc.n_spheres == 1
+    hs.close()
+
+
+@pytest.mark.parametrize("name,fn", [("teapot", scenes_py.teapot_and_ball), ("man", scenes_py.man_and_ball),
+                                     ("bunny", scenes_py.bunny_and_ball)])
+def test_flattener_order_and_pruning_match_oracle_tree(name, fn):
+    """The product's index-based rebuild of bvh.zig:62-185 must give the reference tree: same left-first DFS
+    order of surfaces (tie-break keys) and same set of surfaces hidden under zero-thickness boxes (Q4)."""
+    sc, _ = fn()
+    o_order, o_vis, st = zro_py.bvh_order(sc)
+    with Z.Scene(sc, device=-1) as hs:
+        z_order, z_vis = hs.bvh_order()
+        info = hs.bvh_info()
+        sah = hs.bvh_info(A.ZRT_FLAG_BVH_SAH)
+    assert np.array_equal(o_order, z_order) and np.array_equal(o_vis, z_vis)
+    assert info.reference_nodes == st.bvh_nodes and info.reference_max_depth == st.bvh_max_depth
+    assert info.leaves == int(o_vis.sum()) and info.pruned_surfaces == int((~o_vis).sum())
+    assert info.nodes == info.leaves - 1 and sah.nodes == info.nodes and sah.max_depth <= info.max_depth
+    if name == "man":
+        assert info.pruned_surfaces > 0  # Man.obj has axis-aligned flat triangles

@@ -100,6 +100,7 @@ struct zrt_scene {
     DevBuf<unsigned long long> counters;
     DevBuf<uint32_t> hit_id;
     DevBuf<float> hit_t;
+    uint64_t launch_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -361,6 +362,7 @@ int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d
     }
     if (e_r1) CUDA_TRY(cudaEventRecord(e_r1, st));
     CUDA_TRY(cudaGetLastError());
+    sc->launch_count += *launches;
     return ZRT_OK;
 }
 
@@ -543,6 +545,7 @@ int zrt_primary_hits(zrt_scene *sc, const zrt_camera *camera, const zrt_params *
     plan.P.jitter = jitter ? 1u : 0u;
     launch_primary(plan.P, plan.mode, sc->stream);
     CUDA_TRY(cudaGetLastError());
+    sc->launch_count++;
     CUDA_TRY(cudaMemcpyAsync(surface_id, sc->hit_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->stream));
     CUDA_TRY(cudaMemcpyAsync(t, sc->hit_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
     CUDA_TRY(cudaStreamSynchronize(sc->stream));
@@ -559,6 +562,8 @@ static const FlatBvh *hostBvh(zrt_scene *sc, uint32_t flags) {
     }
     return &sc->host_bvh[k];
 }
+
+uint64_t zrt_scene_launch_count(const zrt_scene *sc) { return sc ? sc->launch_count : 0; }
 
 int zrt_scene_bvh_info(zrt_scene *sc, uint32_t flags, zrt_bvh_info *out) {
     if (!sc || !out) return fail(ZRT_ERR_INVALID, "NULL argument");

@@ -39,6 +39,8 @@ def lib():
         L.zrt_primary_hits.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_int, C.c_void_p, C.c_void_p]
         L.zrt_scene_bvh_info.argtypes = [C.c_void_p, C.c_uint32, P(A.BvhInfo)]
         L.zrt_scene_bvh_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zrt_scene_launch_count.argtypes = [C.c_void_p]
+        L.zrt_scene_launch_count.restype = C.c_uint64
         L.zrt_measure_peaks.argtypes = [C.c_int, P(C.c_double), C.c_int]
         _lib = L
     return _lib
@@ -97,6 +99,9 @@ class Scene:
         t = np.empty((params.height, params.width), np.float32)
         _check(lib().zrt_primary_hits(self._h, C.byref(camera), C.byref(params), jitter, ids.ctypes.data, t.ctypes.data))
         return ids, t
+
+    def launch_count(self):
+        return int(lib().zrt_scene_launch_count(self._h))
 
     def bvh_info(self, flags=0):
         info = A.BvhInfo()
