@@ -308,16 +308,22 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.s_begin = sb; P.s_end = se;
     plan->n_samples = se - sb;
     const uint64_t pixels = (uint64_t)P.x_end * P.height;
-    uint32_t chunks = p->sample_chunks;
-    if (chunks == 0) { // enough threads for ~4 waves of 148 SMs x 1024 resident threads
-        const uint64_t target = 600000;
-        chunks = (uint32_t)((target + pixels - 1) / pixels);
-    }
-    if (chunks > plan->n_samples) chunks = plan->n_samples;
-    if (chunks < 1) chunks = 1;
-    P.chunk_len = (plan->n_samples + chunks - 1) / chunks;
-    if (P.chunk_len == 0) P.chunk_len = 1;
-    P.chunks = plan->n_samples ? (plan->n_samples + P.chunk_len - 1) / P.chunk_len : 1;
+    // L lanes share a pixel's samples (see k_trace): the largest power of two <= min(32, samples), unless
+    // the caller pins it (sample_chunks = 1 reproduces the reference's sequential f32 sum per pixel)
+    uint32_t lanes = p->sample_chunks ? p->sample_chunks : 32u;
+    if (lanes > 32u) lanes = 32u;
+    while (lanes & (lanes - 1u)) lanes &= lanes - 1u;          // round down to a power of two
+    while (lanes > 1u && lanes > plan->n_samples) lanes >>= 1; // every lane gets at least one sample
+    if (lanes < 1u) lanes = 1u;
+    P.lanes = lanes;
+    const uint32_t group = 32u / lanes;
+    // run length: ~32k samples per warp, but at least ~19k warps (4 waves of 148 SMs x 32 resident warps)
+    uint64_t run = plan->n_samples ? (32768ull * group) / ((uint64_t)plan->n_samples * 1u) : group;
+    const uint64_t max_run = pixels / 18944ull;
+    if (run > max_run) run = max_run;
+    run = (run / group) * group;
+    if (run < group) run = group;
+    P.run_len = (uint32_t)run;
     P.max_depth = p->max_depth;
     P.seed32 = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
     P.color_scale = (p->flags & ZRT_FLAG_RAW_SUM) ? 1.0f : 1.0f / (float)p->samples_per_pixel; // raytrace.zig:157
@@ -339,25 +345,33 @@ int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d
     KParams &P = plan.P;
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 6 * sizeof(unsigned long long), st));
     float *trace_out = d_rgb;
-    if (P.chunks > 1) {
-        CUDA_TRY(sc->part.reserve(plan.n_floats * P.chunks));
+    if (P.lanes > 1) {
+        CUDA_TRY(sc->part.reserve(plan.n_floats * P.lanes));
         trace_out = sc->part.p;
     }
     // pixels the reference never writes (x >= height, Q1) stay black: image.zig:80-90
-    if (P.x_end < P.width || P.chunks > 1) CUDA_TRY(cudaMemsetAsync(trace_out, 0, plan.n_floats * P.chunks * sizeof(float), st));
+    if (P.x_end < P.width) CUDA_TRY(cudaMemsetAsync(trace_out, 0, plan.n_floats * P.lanes * sizeof(float), st));
     P.out = trace_out;
     P.counters = d_counters;
     *launches = 0;
     if (e_k0) CUDA_TRY(cudaEventRecord(e_k0, st));
-    if (plan.n_samples > 0) {
+    bool traced = false;
+    if (plan.n_samples > 0 && P.max_depth > 0) {
         launch_trace(P, plan.mode, st);
         (*launches)++;
+        traced = true;
     } else {
+        // no samples, or max_depth = 0: every sample ends at the recursion limit without casting a ray
+        // (raytrace.zig:64-68); the image is black and the counters are known on the host
         CUDA_TRY(cudaMemsetAsync(d_rgb, 0, plan.n_floats * sizeof(float), st));
+        const unsigned long long n_px = (unsigned long long)P.x_end * P.height, n_s = n_px * plan.n_samples;
+        const unsigned long long c[6] = {n_s, 0, 0, P.count_pixels ? n_px : 0ull, n_s, 0};
+        CUDA_TRY(cudaMemcpyAsync(d_counters, c, sizeof(c), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st)); // `c` lives on this stack frame
     }
     if (e_k1) CUDA_TRY(cudaEventRecord(e_k1, st));
-    if (P.chunks > 1) {
-        launch_resolve(sc->part.p, d_rgb, (uint32_t)plan.n_floats, P.chunks, P.color_scale, st);
+    if (traced && P.lanes > 1) {
+        launch_resolve(sc->part.p, d_rgb, (uint32_t)plan.n_floats, P.lanes, P.color_scale, st);
         (*launches)++;
     }
     if (e_r1) CUDA_TRY(cudaEventRecord(e_r1, st));

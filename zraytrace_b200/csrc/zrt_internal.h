@@ -88,7 +88,8 @@ struct KParams {
     float f_width, f_height;
     uint32_t width, height, x_end;
     uint32_t s_begin, s_end; // global sample range of this launch
-    uint32_t chunks, chunk_len; // samples split over `chunks` threads per pixel
+    uint32_t lanes;   // L: lanes that share one pixel's samples (power of two <= 32); partial image slices
+    uint32_t run_len; // pixels walked by one warp, a multiple of 32 / L
     uint32_t max_depth, seed32;
     float color_scale; // 1/spp, or 1 for ZRT_FLAG_RAW_SUM
     uint32_t count_pixels; // 1 if this launch owns sample 0 (pixels_processed is counted once)
