@@ -194,6 +194,11 @@ int zrt_scene_bvh_info(zrt_scene *scene, uint32_t flags, zrt_bvh_info *out);
  * Works on a scene created with device = -1 (host only; such a scene cannot render). */
 int zrt_scene_bvh_order(zrt_scene *scene, uint32_t *order, uint8_t *visible);
 
+/* Device self-test: the exact-quotient fast paths used by the kernels (shared reciprocal + FMA residuals)
+ * against the compiler's IEEE division, over every raytrace.zig:173 numerator of ten image widths and
+ * 2^23 random vectors.  *mismatches must come back 0. */
+int zrt_selftest(int device, uint64_t *mismatches);
+
 /* K0 microbenchmarks that measure the roofline denominators this path is judged against
  * (MEASURED_PEAKS.json has no FP32-issue or L2 number): results in out[0..n).
  *   out[0] fp32 non-FMA op/s (FMUL+FADD chains), out[1] FFMA op/s (1 per instr),

@@ -230,3 +230,9 @@ def test_headline_7spheres_against_published_numbers():
     pool = lambda a: a.reshape(500, 2, 500, 2, 3).mean(axis=(1, 3))
     rmse = np.sqrt(((pool(q) - pool(gold)) ** 2).mean(axis=(0, 1)))
     assert (rmse < 0.01).all(), rmse
+
+
+def test_exact_division_fast_paths_selftest():
+    """The kernels replace `a / b` by a shared IEEE reciprocal + FMA residual corrections; the quotients must be
+    the correctly rounded ones, bit for bit (exhaustive over raytrace.zig:173 numerators for ten widths)."""
+    assert Z.selftest(0) == 0

@@ -19,6 +19,7 @@ namespace zrt {
 void launch_trace(const KParams &P, int mode, cudaStream_t st);
 void launch_primary(const KParams &P, int mode, cudaStream_t st);
 void launch_resolve(const float *part, float *out, uint32_t n, uint32_t chunks, float scale, cudaStream_t st);
+void launch_selftest_div(unsigned long long *mismatch, uint32_t width, uint32_t seed, cudaStream_t st);
 void launch_peak_fp32(float *out, int blocks, int threads, int iters, cudaStream_t st);
 void launch_peak_ffma(float *out, int blocks, int threads, int iters, cudaStream_t st);
 void launch_peak_read(const float4 *src, size_t n4, int passes, float *out, int blocks, int threads, cudaStream_t st);
@@ -192,6 +193,8 @@ int uploadMaterials(zrt_scene *sc) {
         d.kind = m.kind;
         d.ior = m.index_of_refraction;
         d.inv_ior = 1.0f / m.index_of_refraction; // material.zig:111
+        d.r0_front = (1.0f - d.inv_ior) / (1.0f + d.inv_ior); // material.zig:126 with ratio = 1/ior
+        d.r0_back = (1.0f - d.ior) / (1.0f + d.ior);          //                   and ratio = ior
         if (m.kind != ZRT_MATERIAL_DIELECTRIC) {
             const zrt_texture &t = hs.textures[m.texture];
             d.tex_kind = t.kind;
@@ -299,6 +302,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.vx = cam->vertical.x; P.vy = cam->vertical.y; P.vz = cam->vertical.z;
     P.width = p->width; P.height = p->height;
     P.f_width = (float)p->width; P.f_height = (float)p->height; // raytrace.zig:153-154
+    P.rcp_width = 1.0f / P.f_width; P.rcp_height = 1.0f / P.f_height;
     // raytrace.zig:168 `while (x < image.height)`; when height > width the reference writes
     // past the end of the row, which is clamped here
     P.x_end = (p->x_limit == ZRT_XLIMIT_WIDTH) ? p->width : (p->height < p->width ? p->height : p->width);
@@ -597,6 +601,23 @@ int zrt_scene_bvh_order(zrt_scene *sc, uint32_t *order, uint8_t *visible) {
     for (size_t s = 0; s < b->slot_surface.size(); s++) order[s] = b->slot_surface[s];
     std::memset(visible, 0, sc->host.surfaces.size());
     for (size_t s = 0; s < b->slot_surface.size(); s++) visible[b->slot_surface[s]] = b->slot_visible[s];
+    return ZRT_OK;
+}
+
+int zrt_selftest(int device, uint64_t *mismatches) {
+    if (!mismatches) return fail(ZRT_ERR_INVALID, "mismatches is NULL");
+    if (zrt_device_count() == 0) return fail(ZRT_ERR_NO_DEVICE, "no CUDA device visible");
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned long long *d = nullptr, h = 0;
+    CUDA_TRY(cudaMalloc(&d, sizeof(h)));
+    CUDA_TRY(cudaMemset(d, 0, sizeof(h)));
+    const uint32_t widths[] = {1, 7, 200, 512, 1000, 1024, 1080, 1920, 4096, 65535};
+    uint32_t seed = 1;
+    for (uint32_t w : widths) launch_selftest_div(d, w, seed++, 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = h;
     return ZRT_OK;
 }
 

@@ -63,7 +63,7 @@ struct alignas(16) DevMaterial {
     float v_off;
     uint32_t w, h, ch;
     const uint8_t *pixels; // device pointer, rows bottom-up
-    uint64_t pad;
+    float r0_front, r0_back; // dielectric: (1-ratio)/(1+ratio) for ratio = 1/ior and ior (material.zig:126)
 };
 static_assert(sizeof(DevMaterial) == 64, "DevMaterial layout");
 
@@ -86,6 +86,7 @@ struct KParams {
     // camera.zig:11-15
     float ox, oy, oz, llx, lly, llz, hx, hy, hz, vx, vy, vz;
     float f_width, f_height;
+    float rcp_width, rcp_height; // RN(1/width), RN(1/height) for the exact quotients of raytrace.zig:173-174
     uint32_t width, height, x_end;
     uint32_t s_begin, s_end; // global sample range of this launch
     uint32_t lanes;   // L: lanes that share one pixel's samples (power of two <= 32); partial image slices

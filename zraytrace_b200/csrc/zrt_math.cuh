@@ -10,8 +10,9 @@
 //
 //   sincos : Cephes single-precision scheme: j = trunc(x * 4/pi) rounded up to even, 3-term Cody-Waite
 //            reduction by j*pi/4, degree-3 polynomials in z^2, octant fix-up.  Domain 0 <= x <= 8192.
-//   acos   : FreeBSD msun e_acosf.c scheme: rational R(z)=p/q; sqrt split for |x| > 0.5.
-//   atan2  : FreeBSD msun s_atanf.c / e_atan2f.c scheme: four reduction ranges with hi/lo constants.
+//   acos   : Abramowitz & Stegun 4.4.46: sqrt(1-|x|) * P7(|x|), reflected for x < 0.  Branch-free.
+//   atan2  : octant folding t = min/max in [0,1], Abramowitz & Stegun 4.4.49 odd polynomial, three
+//            reflections.  Branch-free (it runs inside a divergent region).
 //   pow5   : Zig's std.math.pow evaluates an integer power by square-and-multiply on the mantissa with
 //            exact power-of-two scaling, i.e. x^5 = x * ((x*x) * (x*x)) in plain f32 products.
 #pragma once
@@ -42,111 +43,57 @@ __device__ __forceinline__ void sincos_spec(float x, float *s_out, float *c_out)
     *c_out = (q == 1 || q == 2) ? -b : b;
 }
 
-__device__ __forceinline__ float acos_R(float z) {
-    const float pS0 = 1.6666586697e-01f, pS1 = -4.2743422091e-02f, pS2 = -8.6563630030e-03f, qS1 = -7.0662963390e-01f;
-    const float p = z * (pS0 + z * (pS1 + z * pS2));
-    const float q = 1.0f + z * qS1;
-    return p / q;
+// ---- exact IEEE division helpers ---------------------------------------------------------------------
+// a / b correctly rounded (round-to-nearest-even), given y = RN(1/b): two FMA residual corrections
+// (Markstein).  Preconditions (callers guarantee them): b finite and normal, a == 0 or 2^-60 <= |a| and the
+// quotient far from overflow/underflow, so that both residuals are exact.  The sign of a zero quotient
+// is the IEEE one.  tests/ check it bit for bit against the compiler's own division.
+__device__ __forceinline__ float div_exact(float a, float b, float y) {
+    const float q0 = a * y;
+    const float r0 = __fmaf_rn(-b, q0, a);
+    const float q1 = __fmaf_rn(r0, y, q0);
+    const float r1 = __fmaf_rn(-b, q1, a);
+    const float q2 = __fmaf_rn(r1, y, q1);
+    return (a == 0.0f) ? q0 : q2;
 }
 
 __device__ __forceinline__ float acos_spec(float x) {
-    const float pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f;
-    const unsigned hx = __float_as_uint(x);
-    const unsigned ix = hx & 0x7fffffffu;
-    if (ix >= 0x3f800000u) {
-        if (ix == 0x3f800000u) {
-            if (hx >> 31) return 2 * pio2_hi + 7.5231638452626401e-37f;
-            return 0.0f;
-        }
-        return __uint_as_float(0x7fc00000u);
-    }
-    if (ix < 0x3f000000u) {
-        if (ix <= 0x32800000u) return pio2_hi + 7.5231638452626401e-37f;
-        return pio2_hi - (x - (pio2_lo - x * acos_R(x * x)));
-    }
-    if (hx >> 31) {
-        const float z = (1 + x) * 0.5f;
-        const float s = sqrtf(z);
-        const float w = acos_R(z) * s - pio2_lo;
-        return 2 * (pio2_hi - (s + w));
-    }
-    const float z = (1 - x) * 0.5f;
-    const float s = sqrtf(z);
-    const float df = __uint_as_float(__float_as_uint(s) & 0xfffff000u);
-    const float c = (z - df * df) / (s + df);
-    const float w = acos_R(z) * s + c;
-    return 2 * (df + w);
+    const float ax = fabsf(x);
+    float p = -0.0012624911f;
+    p = p * ax + 0.0066700901f;
+    p = p * ax + -0.0170881256f;
+    p = p * ax + 0.0308918810f;
+    p = p * ax + -0.0501743046f;
+    p = p * ax + 0.0889789874f;
+    p = p * ax + -0.2145988016f;
+    p = p * ax + 1.5707963050f;
+    const float r = sqrtf(1.0f - ax) * p;
+    return (x < 0.0f) ? 3.14159265358979323846f - r : r;
 }
 
-__device__ __forceinline__ float atan_spec(float x) {
-    const float aT0 = 3.3333328366e-01f, aT1 = -1.9999158382e-01f, aT2 = 1.4253635705e-01f, aT3 = -1.0648017377e-01f,
-                aT4 = 6.1687607318e-02f;
-    unsigned ix = __float_as_uint(x);
-    const unsigned sign = ix >> 31;
-    ix &= 0x7fffffffu;
-    float hi = 0.0f, lo = 0.0f;
-    bool reduced = true;
-    if (ix >= 0x4c800000u) {
-        if (ix > 0x7f800000u) return x;
-        const float z = 1.5707962513e+00f + 7.5231638452626401e-37f;
-        return sign ? -z : z;
-    }
-    if (ix < 0x3ee00000u) {
-        if (ix < 0x39800000u) return x;
-        reduced = false;
-    } else {
-        x = fabsf(x);
-        if (ix < 0x3f980000u) {
-            if (ix < 0x3f300000u) {
-                hi = 4.6364760399e-01f; lo = 5.0121582440e-09f;
-                x = (2.0f * x - 1.0f) / (2.0f + x);
-            } else {
-                hi = 7.8539812565e-01f; lo = 3.7748947079e-08f;
-                x = (x - 1.0f) / (x + 1.0f);
-            }
-        } else {
-            if (ix < 0x401c0000u) {
-                hi = 9.8279368877e-01f; lo = 3.4473217170e-08f;
-                x = (x - 1.5f) / (1.0f + 1.5f * x);
-            } else {
-                hi = 1.5707962513e+00f; lo = 7.5497894159e-08f;
-                x = -1.0f / x;
-            }
-        }
-    }
-    const float z = x * x;
-    const float w = z * z;
-    const float s1 = z * (aT0 + w * (aT2 + w * aT4));
-    const float s2 = w * (aT1 + w * aT3);
-    if (!reduced) return x - x * (s1 + s2);
-    const float r = hi - ((x * (s1 + s2) - lo) - x);
-    return sign ? -r : r;
+__device__ __forceinline__ float atan01_spec(float t) {
+    const float s = t * t;
+    float p = 0.0028662257f;
+    p = p * s + -0.0161657367f;
+    p = p * s + 0.0429096138f;
+    p = p * s + -0.0752896400f;
+    p = p * s + 0.1065626393f;
+    p = p * s + -0.1420889944f;
+    p = p * s + 0.1999355085f;
+    p = p * s + -0.3333314528f;
+    p = p * s + 1.0f;
+    return p * t;
 }
 
 __device__ __forceinline__ float atan2_spec(float y, float x) {
-    const float pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
-    if (isnan(x) || isnan(y)) return x + y;
-    unsigned ix = __float_as_uint(x), iy = __float_as_uint(y);
-    if (ix == 0x3f800000u) return atan_spec(y);
-    const unsigned m = ((iy >> 31) & 1) | ((ix >> 30) & 2);
-    ix &= 0x7fffffffu;
-    iy &= 0x7fffffffu;
-    if (iy == 0) return (m == 0 || m == 1) ? y : (m == 2 ? pi : -pi);
-    if (ix == 0) return (m & 1) ? -pi / 2 : pi / 2;
-    if (ix == 0x7f800000u) {
-        if (iy == 0x7f800000u) return m == 0 ? pi / 4 : (m == 1 ? -pi / 4 : (m == 2 ? 3 * pi / 4 : -3 * pi / 4));
-        return m == 0 ? 0.0f : (m == 1 ? -0.0f : (m == 2 ? pi : -pi));
-    }
-    if (ix + (26u << 23) < iy || iy == 0x7f800000u) return (m & 1) ? -pi / 2 : pi / 2;
-    float z;
-    if ((m & 2) && iy + (26u << 23) < ix) z = 0.0f;
-    else z = atan_spec(fabsf(y / x));
-    switch (m) {
-    case 0: return z;
-    case 1: return -z;
-    case 2: return pi - (z - pi_lo);
-    default: return (z - pi_lo) - pi;
-    }
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = (ax > ay) ? ax : ay, mn = (ax > ay) ? ay : ax;
+    const float t = (mx == 0.0f) ? 0.0f : mn / mx;
+    float p = atan01_spec(t);
+    if (ay > ax) p = 1.57079632679489661923f - p;
+    if (x < 0.0f) p = 3.14159265358979323846f - p;
+    if (y < 0.0f) p = -p;
+    return p;
 }
 
 __device__ __forceinline__ float pow5_spec(float x) {

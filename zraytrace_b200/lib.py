@@ -41,6 +41,7 @@ def lib():
         L.zrt_scene_bvh_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.zrt_scene_launch_count.argtypes = [C.c_void_p]
         L.zrt_scene_launch_count.restype = C.c_uint64
+        L.zrt_selftest.argtypes = [C.c_int, P(C.c_uint64)]
         L.zrt_measure_peaks.argtypes = [C.c_int, P(C.c_double), C.c_int]
         _lib = L
     return _lib
@@ -113,6 +114,13 @@ class Scene:
         vis = np.zeros(self.n_surfaces, np.uint8)
         _check(lib().zrt_scene_bvh_order(self._h, order.ctypes.data, vis.ctypes.data))
         return order, vis.astype(bool)
+
+
+def selftest(device=0):
+    """-> number of bit mismatches between the kernels' exact-division fast paths and IEEE division (must be 0)"""
+    n = C.c_uint64()
+    _check(lib().zrt_selftest(device, C.byref(n)))
+    return int(n.value)
 
 
 def measure_peaks(device=0):
