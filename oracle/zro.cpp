@@ -695,7 +695,8 @@ void renderRows(const Scene &sc, const zrt_camera *camera, const zrt_params *p, 
                 color_acc = cadd(color_acc, color);
                 progress->samples_processed += 1;
             }
-            progress->pixels_processed += 1;
+            if (s_begin == 0) progress->pixels_processed += 1; // a partial sample range (multi-GPU split) counts the
+                                                               // pixel once, on the call that owns sample 0
             const Color px = cscale(color_acc, color_scale);
             float *o = out_rgb + ((size_t)y * p->width + x) * 3;
             o[0] = px.r; o[1] = px.g; o[2] = px.b;
