@@ -42,6 +42,23 @@ int fail(int code, const std::string &msg) {
             return fail(ZRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
     } while (0)
 
+// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync) with the release
+// threshold raised, so creating and destroying scenes or scratch images does not pay cudaMalloc/cudaFree
+// (the 100+ ms spikes seen in the first end-to-end measurements) after the first use.
+cudaStream_t g_alloc_stream(int device) {
+    static cudaStream_t streams[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!streams[device]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+    }
+    return streams[device];
+}
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -53,13 +70,22 @@ struct DevBuf {
     }
     cudaError_t reserve(size_t count) {
         if (count <= n) return cudaSuccess;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaStream_t st = g_alloc_stream(dev);
         release();
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st); // usable from any stream afterwards
         if (e == cudaSuccess) n = count;
+        else p = nullptr;
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaFreeAsync(p, g_alloc_stream(dev));
+        }
         p = nullptr;
         n = 0;
     }
@@ -92,14 +118,14 @@ struct zrt_scene {
     HostScene host;
     bool all_spheres = false;
     DevBuf<DevMaterial> mats;
-    std::vector<uint8_t *> d_texels;
+    std::vector<DevBuf<uint8_t>> d_texels;
     DevRep rep_list, rep_bvh, rep_sah;
     FlatBvh host_bvh[2]; // host-only inspection (device == -1)
     bool host_bvh_ready[2] = {false, false};
     // scratch owned by the scene
     DevBuf<float> part, image;
     DevBuf<unsigned long long> counters;
-    DevBuf<uint32_t> hit_id;
+    DevBuf<uint32_t> hit_id, work;
     DevBuf<float> hit_t;
     uint64_t launch_count = 0;
     cudaStream_t stream = nullptr;
@@ -180,12 +206,10 @@ int validate(const zrt_scene_desc *d) {
 int uploadMaterials(zrt_scene *sc) {
     const HostScene &hs = sc->host;
     std::vector<DevMaterial> mats(hs.materials.size());
-    sc->d_texels.assign(hs.textures.size(), nullptr);
+    sc->d_texels.resize(hs.textures.size());
     for (size_t i = 0; i < hs.textures.size(); i++) {
         if (hs.textures[i].kind != ZRT_TEXTURE_IMAGE) continue;
-        const size_t bytes = hs.texels[i].size();
-        CUDA_TRY(cudaMalloc(&sc->d_texels[i], bytes));
-        CUDA_TRY(cudaMemcpy(sc->d_texels[i], hs.texels[i].data(), bytes, cudaMemcpyHostToDevice));
+        CUDA_TRY(sc->d_texels[i].upload(hs.texels[i]));
     }
     for (size_t i = 0; i < mats.size(); i++) {
         const zrt_material &m = hs.materials[i];
@@ -201,7 +225,7 @@ int uploadMaterials(zrt_scene *sc) {
             d.r = t.r; d.g = t.g; d.b = t.b;
             d.u_off = t.u_offset; d.v_off = t.v_offset;
             d.w = t.width; d.h = t.height; d.ch = t.channels;
-            d.pixels = sc->d_texels[m.texture];
+            d.pixels = sc->d_texels[m.texture].p;
         }
         mats[i] = d;
     }
@@ -312,22 +336,24 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.s_begin = sb; P.s_end = se;
     plan->n_samples = se - sb;
     const uint64_t pixels = (uint64_t)P.x_end * P.height;
-    // L lanes share a pixel's samples (see k_trace): the largest power of two <= min(32, samples), unless
-    // the caller pins it (sample_chunks = 1 reproduces the reference's sequential f32 sum per pixel)
-    uint32_t lanes = p->sample_chunks ? p->sample_chunks : 32u;
+    // L slices per pixel (see k_trace): 8 measured best on C5 at 125..1000 spp (items of 16..125 samples), more
+    // only when the image is so small that 8 would leave resident warps without items (~1.2 M items wanted);
+    // the caller can pin it (sample_chunks = 1 reproduces the reference's sequential f32 sum per pixel)
+    uint32_t lanes = p->sample_chunks;
+    if (lanes == 0) {
+        const uint32_t by_samples = 8u;
+        const uint64_t by_items = (1200000ull + pixels - 1) / (pixels ? pixels : 1);
+        lanes = (uint32_t)(by_samples > by_items ? by_samples : by_items);
+        uint32_t p2 = 1;
+        while (p2 < lanes && p2 < 32u) p2 <<= 1; // round up to a power of two
+        lanes = p2;
+    }
     if (lanes > 32u) lanes = 32u;
     while (lanes & (lanes - 1u)) lanes &= lanes - 1u;          // round down to a power of two
-    while (lanes > 1u && lanes > plan->n_samples) lanes >>= 1; // every lane gets at least one sample
+    while (lanes > 1u && lanes > plan->n_samples) lanes >>= 1; // every slice gets at least one sample
     if (lanes < 1u) lanes = 1u;
+    if (pixels * lanes > 0xFFFFFF00ull) return fail(ZRT_ERR_INVALID, "image too large");
     P.lanes = lanes;
-    const uint32_t group = 32u / lanes;
-    // run length: ~32k samples per warp, but at least ~19k warps (4 waves of 148 SMs x 32 resident warps)
-    uint64_t run = plan->n_samples ? (32768ull * group) / ((uint64_t)plan->n_samples * 1u) : group;
-    const uint64_t max_run = pixels / 18944ull;
-    if (run > max_run) run = max_run;
-    run = (run / group) * group;
-    if (run < group) run = group;
-    P.run_len = (uint32_t)run;
     P.max_depth = p->max_depth;
     P.seed32 = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
     P.color_scale = (p->flags & ZRT_FLAG_RAW_SUM) ? 1.0f : 1.0f / (float)p->samples_per_pixel; // raytrace.zig:157
@@ -357,6 +383,9 @@ int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d
     if (P.x_end < P.width) CUDA_TRY(cudaMemsetAsync(trace_out, 0, plan.n_floats * P.lanes * sizeof(float), st));
     P.out = trace_out;
     P.counters = d_counters;
+    CUDA_TRY(sc->work.reserve(1));
+    CUDA_TRY(cudaMemsetAsync(sc->work.p, 0, sizeof(uint32_t), st));
+    P.work_counter = sc->work.p;
     *launches = 0;
     if (e_k0) CUDA_TRY(cudaEventRecord(e_k0, st));
     bool traced = false;
@@ -466,9 +495,8 @@ void zrt_scene_destroy(zrt_scene *sc) {
         if (sc->stream) cudaStreamSynchronize(sc->stream);
         sc->rep_list.release(); sc->rep_bvh.release(); sc->rep_sah.release();
         sc->mats.release(); sc->part.release(); sc->image.release(); sc->counters.release();
-        sc->hit_id.release(); sc->hit_t.release();
-        for (uint8_t *p : sc->d_texels)
-            if (p) cudaFree(p);
+        sc->hit_id.release(); sc->hit_t.release(); sc->work.release();
+        for (auto &t : sc->d_texels) t.release();
         for (auto &e : sc->ev)
             if (e) cudaEventDestroy(e);
         if (sc->stream) cudaStreamDestroy(sc->stream);

@@ -89,8 +89,8 @@ struct KParams {
     float rcp_width, rcp_height; // RN(1/width), RN(1/height) for the exact quotients of raytrace.zig:173-174
     uint32_t width, height, x_end;
     uint32_t s_begin, s_end; // global sample range of this launch
-    uint32_t lanes;   // L: lanes that share one pixel's samples (power of two <= 32); partial image slices
-    uint32_t run_len; // pixels walked by one warp, a multiple of 32 / L
+    uint32_t lanes;   // L: slices per pixel (power of two <= 32); a work item is (pixel, slice)
+    uint32_t *work_counter; // global item queue head, zeroed before the launch
     uint32_t max_depth, seed32;
     float color_scale; // 1/spp, or 1 for ZRT_FLAG_RAW_SUM
     uint32_t count_pixels; // 1 if this launch owns sample 0 (pixels_processed is counted once)
