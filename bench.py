@@ -195,7 +195,7 @@ def run_zrt(args, wl_name, wl):
         dist.init_process_group("nccl", device_id=dev)
 
     hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0))
-    flags = A.ZRT_FLAG_BVH_SAH if (args.sah and wl_name in ("c2", "c3", "c4")) else 0
+    flags = A.ZRT_FLAG_BVH_REFERENCE if args.reftree else 0
     params = params_for(wl, flags=flags)
     scene = Z.Scene(hs, device=local_rank)
     accum = torch.empty((wl["h"], wl["w"], 3), dtype=torch.float32, device=dev)
@@ -292,7 +292,7 @@ def run_zrt(args, wl_name, wl):
                        "rays_per_step": rays_per_step, "samples_per_step": int(cnt[4]),
                        "l2": "256 MiB device memset between timed steps (outside the per-step event pairs); "
                              "scene data is <= a few MB and stays cache resident by design",
-                       "bvh": "binned-SAH" if flags else "reference tree", "seed": 42,
+                       "bvh": ("reference topology" if flags else "binned SAH over the reference's surviving primitives") if wl_name in ("c2", "c3", "c4") else "none (surface list)", "seed": 42,
                        "wall_s_timed_region": t_wall},
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": rays_per_step / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="zrt", choices=["zrt", "reference"])
-    ap.add_argument("--sah", action="store_true", help="BVH workloads: traverse the binned-SAH tree")
+    ap.add_argument("--reftree", action="store_true", help="BVH workloads: traverse the reference topology, not the SAH tree")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

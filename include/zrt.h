@@ -118,8 +118,10 @@ typedef struct zrt_params {
 enum {
     ZRT_FLAG_RAW_SUM = 1u << 0, /* output the un-normalised sum over the traced samples (for multi-GPU
                                    reduction) instead of sum * (1/samples_per_pixel) raytrace.zig:157,182 */
-    ZRT_FLAG_BVH_SAH = 1u << 1  /* traverse a binned-SAH tree built by libzrt instead of the flattened
-                                   reference tree; hits are identical (tie-break on reference DFS order) */
+    ZRT_FLAG_BVH_REFERENCE = 1u << 1 /* traverse the flattened topology of the reference's own tree
+                                   (bvh.zig:62-185) instead of the binned-SAH tree libzrt builds by default over
+                                   the same primitives; hits are identical either way (ties break on the
+                                   reference DFS order, unreachable surfaces are pruned), only speed differs */
 };
 
 /* raytrace.zig:20-34 Progress (the six u64 counters), same semantics */

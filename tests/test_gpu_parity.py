@@ -65,12 +65,13 @@ def test_primary_hits_bit_exact(built, name, size, jitter):
 
 
 @pytest.mark.parametrize("name", ["teapot", "bunny", "man"])
-def test_primary_hits_sah_tree_same_hits(built, name):
-    """ZRT_FLAG_BVH_SAH changes the tree, not the answer (ties break on the reference DFS order)."""
+def test_primary_hits_reference_topology_same_hits(built, name):
+    """ZRT_FLAG_BVH_REFERENCE changes the tree that is traversed, not the answer (ties break on the reference
+    DFS order in both)."""
     sc, cam, dev = built(name)
     p = A.make_params(160, 160, 1, 30)
     ids_o, t_o = zro_py.primary_hits(sc, cam, p)
-    p.flags = A.ZRT_FLAG_BVH_SAH
+    p.flags = A.ZRT_FLAG_BVH_REFERENCE
     ids_g, t_g = dev.primary_hits(cam, p)
     assert np.array_equal(ids_o, ids_g)
     assert np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32))
@@ -113,11 +114,11 @@ def test_full_paths_match_oracle_draw_for_draw(built, name, w, spp, depth):
     assert tm.launches >= 1 and tm.kernel_ms > 0
 
 
-def test_sah_tree_full_paths(built):
+def test_reference_topology_full_paths(built):
     sc, cam, dev = built("teapot")
     p = A.make_params(64, 64, 8, 30, sample_chunks=1)
     img_o, c_o, _ = zro_py.render(sc, cam, p)
-    p.flags = A.ZRT_FLAG_BVH_SAH
+    p.flags = A.ZRT_FLAG_BVH_REFERENCE
     img_g, c_g, _ = dev.render(cam, p)
     _counters_equal(c_o, c_g)
     np.testing.assert_allclose(img_g, img_o, rtol=2e-5, atol=1e-6)

@@ -150,8 +150,8 @@ def test_flattener_order_and_pruning_match_oracle_tree(name, fn):
     o_order, o_vis, st = zro_py.bvh_order(sc)
     with Z.Scene(sc, device=-1) as hs:
         z_order, z_vis = hs.bvh_order()
-        info = hs.bvh_info()
-        sah = hs.bvh_info(A.ZRT_FLAG_BVH_SAH)
+        info = hs.bvh_info(A.ZRT_FLAG_BVH_REFERENCE)
+        sah = hs.bvh_info()
     assert np.array_equal(o_order, z_order) and np.array_equal(o_vis, z_vis)
     assert info.reference_nodes == st.bvh_nodes and info.reference_max_depth == st.bvh_max_depth
     assert info.leaves == int(o_vis.sum()) and info.pruned_surfaces == int((~o_vis).sum())

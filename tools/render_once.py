@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Render one workload a few times through the C ABI and print timing; the short command used under ncu.
-  python tools/render_once.py --workload c5 [--spp N] [--reps R] [--sah] [--chunks C]"""
+  python tools/render_once.py --workload c5 [--spp N] [--reps R] [--reftree] [--chunks C]"""
 import argparse
 import json
 import os
@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c5")
 ap.add_argument("--spp", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--sah", action="store_true")
+ap.add_argument("--reftree", action="store_true")
 ap.add_argument("--chunks", type=int, default=0)
 ap.add_argument("--primary", action="store_true")
 a = ap.parse_args()
@@ -23,7 +23,7 @@ wl = dict(bench.WORKLOADS[a.workload])
 if a.spp:
     wl["spp"] = a.spp
 hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0))
-p = bench.params_for(wl, flags=A.ZRT_FLAG_BVH_SAH if a.sah else 0, sample_chunks=a.chunks)
+p = bench.params_for(wl, flags=A.ZRT_FLAG_BVH_REFERENCE if a.reftree else 0, sample_chunks=a.chunks)
 with Z.Scene(hs, device=0) as sc:
     for i in range(a.reps):
         if a.primary:

@@ -266,7 +266,7 @@ int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
     const HostScene &hs = sc->host;
     build_flat_bvh(hs, sah, &r.info);
     if (r.info.max_depth + 2 >= (uint32_t)TRAVERSAL_STACK)
-        return fail(ZRT_ERR_INVALID, "BVH deeper than the traversal stack; retry with ZRT_FLAG_BVH_SAH");
+        return fail(ZRT_ERR_INVALID, "BVH deeper than the traversal stack; drop ZRT_FLAG_BVH_REFERENCE");
     const uint32_t slots = (uint32_t)r.info.slot_surface.size();
     std::vector<float4> A(slots), E1(slots), E2(slots);
     std::vector<TriMeta> meta(slots);
@@ -296,7 +296,7 @@ int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
 // raytrace.zig:111-133 preprocessSufraces: BVH iff flag and more than 10 surfaces
 int selectRep(zrt_scene *sc, const zrt_params *p, DevRep **out) {
     const bool use_bvh = p->bounded_volume_hierarchy != 0 && sc->host.surfaces.size() > 10;
-    DevRep *r = !use_bvh ? &sc->rep_list : ((p->flags & ZRT_FLAG_BVH_SAH) ? &sc->rep_sah : &sc->rep_bvh);
+    DevRep *r = !use_bvh ? &sc->rep_list : ((p->flags & ZRT_FLAG_BVH_REFERENCE) ? &sc->rep_bvh : &sc->rep_sah);
     if (!r->ready) {
         const auto t0 = std::chrono::steady_clock::now();
         const int rc = !use_bvh ? buildListRep(sc, *r) : buildBvhRep(sc, *r, r == &sc->rep_sah);
@@ -599,7 +599,7 @@ int zrt_primary_hits(zrt_scene *sc, const zrt_camera *camera, const zrt_params *
 }
 
 static const FlatBvh *hostBvh(zrt_scene *sc, uint32_t flags) {
-    const int k = (flags & ZRT_FLAG_BVH_SAH) ? 1 : 0;
+    const int k = (flags & ZRT_FLAG_BVH_REFERENCE) ? 0 : 1;
     DevRep &r = k ? sc->rep_sah : sc->rep_bvh;
     if (r.ready) return &r.info;
     if (!sc->host_bvh_ready[k]) {

@@ -8,7 +8,7 @@
 //      * a node whose box has zero thickness on an axis is never entered, because
 //        aabb.zig:121 rejects on `tmax <= tmin`                            -> pruning
 // 2. Flatten what survives into 64-byte two-child nodes (DevNode) in DFS pre-order.
-// 3. Optionally (ZRT_FLAG_BVH_SAH) throw the reference topology away and re-split the surviving
+// 3. By default (unless ZRT_FLAG_BVH_REFERENCE) throw the reference topology away and re-split the surviving
 //    primitives with a binned surface-area heuristic; slots keep the reference order, so the hits
 //    are the same and only the number of node fetches changes.
 #include <algorithm>
@@ -212,10 +212,8 @@ struct Flattener {
     }
     void writeNode(uint32_t idx, const Emitted &l, const Emitted &r) {
         DevNode &d = out->nodes[idx];
-        for (int k = 0; k < 3; k++) {
-            d.lmin[k] = l.box.mn[k]; d.lmax[k] = l.box.mx[k];
-            d.rmin[k] = r.box.mn[k]; d.rmax[k] = r.box.mx[k];
-        }
+        d.set_box(0, l.box.mn, l.box.mx);
+        d.set_box(1, r.box.mn, r.box.mx);
         d.left = l.ref; d.right = r.ref; d.pad0 = d.pad1 = 0;
     }
 };
@@ -298,10 +296,8 @@ struct SahBuilder {
         const Emitted l = build(ids, mid, depth + 1);
         const Emitted r = build(ids + mid, n - mid, depth + 1);
         DevNode &d = (*nodes)[my];
-        for (int k = 0; k < 3; k++) {
-            d.lmin[k] = l.box.mn[k]; d.lmax[k] = l.box.mx[k];
-            d.rmin[k] = r.box.mn[k]; d.rmax[k] = r.box.mx[k];
-        }
+        d.set_box(0, l.box.mn, l.box.mx);
+        d.set_box(1, r.box.mn, r.box.mx);
         d.left = l.ref; d.right = r.ref; d.pad0 = d.pad1 = 0;
         return Emitted{my, boxUnion(l.box, r.box)};
     }

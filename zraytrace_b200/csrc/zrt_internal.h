@@ -67,14 +67,19 @@ struct alignas(16) DevMaterial {
 };
 static_assert(sizeof(DevMaterial) == 64, "DevMaterial layout");
 
-// 64-byte BVH node, cache-line-half aligned, read as four 128-bit loads.
-//   q0 = (lmin.x, lmin.y, lmin.z, lmax.x)
-//   q1 = (lmax.y, lmax.z, rmin.x, rmin.y)
-//   q2 = (rmin.z, rmax.x, rmax.y, rmax.z)
+// 64-byte BVH node, 64-byte aligned, read as four 128-bit loads.  Left and right child boxes are interleaved
+// so that every float2 is a (left, right) pair ready for the packed f32x2 slab test:
+//   q0 = (lmin.x, rmin.x, lmin.y, rmin.y)
+//   q1 = (lmin.z, rmin.z, lmax.x, rmax.x)
+//   q2 = (lmax.y, rmax.y, lmax.z, rmax.z)
 //   q3 = (left_ref, right_ref, -, -)
 struct alignas(64) DevNode {
-    float lmin[3], lmax[3], rmin[3], rmax[3];
+    float mn_x[2], mn_y[2], mn_z[2], mx_x[2], mx_y[2], mx_z[2]; // [0] = left child, [1] = right child
     uint32_t left, right, pad0, pad1;
+    void set_box(int child, const float mn[3], const float mx[3]) {
+        mn_x[child] = mn[0]; mn_y[child] = mn[1]; mn_z[child] = mn[2];
+        mx_x[child] = mx[0]; mx_y[child] = mx[1]; mx_z[child] = mx[2];
+    }
 };
 static_assert(sizeof(DevNode) == 64, "DevNode layout");
 
