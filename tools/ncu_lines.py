@@ -56,7 +56,7 @@ print(f"total warp-inst {tot[0]:.4g} thread-inst {tot[1]:.4g} avg active {tot[1]
 for key, g in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     f, ln = key if key else ("?", 0)
     if f not in src and f != "?":
-        p = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", f)
+        p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "zraytrace_b200", "csrc", f)
         src[f] = open(p).read().splitlines() if os.path.exists(p) else []
     text = src.get(f, [])[ln - 1].strip()[:90] if f in src and 0 < ln <= len(src[f]) else ""
     print(f"{f}:{ln:4d} sass={g[3]:4d} winst={100*g[0]/tot[0]:5.1f}% active={g[1]/max(g[0],1):5.1f} stall={100*g[2]/max(tot[2],1):5.1f}%  {text}")
