@@ -307,7 +307,26 @@ def run_zrt(args, wl_name, wl):
     else:
         ops_per_ray = {"c1": 216.0, "c5": 216.0}.get(wl_name)
         bytes_per_ray = None
-    if ops_per_ray:
+    is_bvh = wl_name in ("c2", "c3", "c4")
+    if is_bvh:
+        # byte side: event counts from the instrumented build of the same kernel on this rank's share
+        st = scene.trace_statistics(hs.camera, p_rank)
+        alg_bytes = (64 * st.node_visits + 48 * st.triangle_tests + 32 * st.sphere_tests + 12 * st.samples
+                     + 4 * st.texture_lookups)
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        peak = peaks["l2_read_gbs"]
+        line["roofline"] = {"bound": "l2", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "kernel": "k_trace", "kernel_ms": kernel_ms, "rays_per_launch": rays_rank,
+                            "algorithmic_bytes_per_ray": alg_bytes / max(st.rays, 1),
+                            "events_per_ray": {"node_visits": st.node_visits / max(st.rays, 1),
+                                               "triangle_tests": st.triangle_tests / max(st.rays, 1),
+                                               "sphere_tests": st.sphere_tests / max(st.rays, 1)},
+                            "peak_source": "L2-resident 128-bit read bandwidth measured in this run by zrt_measure_peaks "
+                                           "(MEASURED_PEAKS.json has no L2 figure); scene data is L1/L2 resident, HBM is idle",
+                            "k0": peaks, "hbm_peak_gbs": peaks_file.get("hbm_gbs"), "hbm_peak_source": peaks_src,
+                            "fp32_ops_per_ray_reference_tree": ops_per_ray,
+                            "mrays_per_s_kernel_only": rays_rank / (kernel_ms * 1e-3) / 1e6}
+    elif ops_per_ray:
         achieved = ops_per_ray * rays_rank / (kernel_ms * 1e-3) / 1e12
         peak = peaks["fp32_nofma_ops"] / 1e12
         line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

@@ -196,6 +196,14 @@ int zrt_scene_bvh_info(zrt_scene *scene, uint32_t flags, zrt_bvh_info *out);
  * Works on a scene created with device = -1 (host only; such a scene cannot render). */
 int zrt_scene_bvh_order(zrt_scene *scene, uint32_t *order, uint8_t *visible);
 
+/* Event counts of one render, measured by an instrumented build of the same kernel (slower; the image is
+ * discarded).  They are the byte side of the roofline: 64 B per node visit, 48 B per triangle test, 32 B per
+ * sphere test, 3-4 B per texture lookup, 12 B per sample (DESIGN.md "Measurement"). */
+typedef struct zrt_trace_stats {
+    uint64_t rays, samples, node_visits, triangle_tests, sphere_tests, texture_lookups;
+} zrt_trace_stats;
+int zrt_trace_statistics(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params, zrt_trace_stats *out);
+
 /* Device self-test: the exact-quotient fast paths used by the kernels (shared reciprocal + FMA residuals)
  * against the compiler's IEEE division, over every raytrace.zig:173 numerator of ten image widths and
  * 2^23 random vectors.  *mismatches must come back 0. */

@@ -78,6 +78,14 @@ class Timing(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class TraceStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "samples", "node_visits", "triangle_tests", "sphere_tests",
+                                          "texture_lookups")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 class BvhInfo(C.Structure):
     _fields_ = [("nodes", C.c_uint32), ("leaves", C.c_uint32), ("max_depth", C.c_uint32),
                 ("pruned_surfaces", C.c_uint32), ("reference_nodes", C.c_uint32),

@@ -632,6 +632,35 @@ int zrt_scene_bvh_order(zrt_scene *sc, uint32_t *order, uint8_t *visible) {
     return ZRT_OK;
 }
 
+int zrt_trace_statistics(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, zrt_trace_stats *out) {
+    int rc = requireDevice(sc);
+    if (rc != ZRT_OK) return rc;
+    if (!out || !params) return fail(ZRT_ERR_INVALID, "NULL argument");
+    DevRep *rep = nullptr;
+    rc = selectRep(sc, params, &rep);
+    if (rc != ZRT_OK) return rc;
+    Plan plan;
+    rc = makePlan(sc, camera, params, rep, &plan);
+    if (rc != ZRT_OK) return rc;
+    CUDA_TRY(sc->image.reserve(plan.n_floats));
+    CUDA_TRY(sc->counters.reserve(6 + 4));
+    CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 10 * sizeof(unsigned long long), sc->stream));
+    plan.P.stats = sc->counters.p + 6;
+    uint32_t launches = 0;
+    rc = enqueueRender(sc, plan, sc->image.p, sc->counters.p, sc->stream, nullptr, nullptr, nullptr, &launches);
+    if (rc != ZRT_OK) return rc;
+    unsigned long long h[10];
+    CUDA_TRY(cudaMemcpyAsync(h, sc->counters.p, sizeof(h), cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    out->rays = h[5];
+    out->samples = h[4];
+    out->node_visits = h[6];
+    out->triangle_tests = h[7];
+    out->sphere_tests = h[8];
+    out->texture_lookups = h[9];
+    return ZRT_OK;
+}
+
 int zrt_selftest(int device, uint64_t *mismatches) {
     if (!mismatches) return fail(ZRT_ERR_INVALID, "mismatches is NULL");
     if (zrt_device_count() == 0) return fail(ZRT_ERR_NO_DEVICE, "no CUDA device visible");

@@ -112,6 +112,7 @@ struct KParams {
     // outputs
     float *out;                   // [chunks][height][width][3]
     unsigned long long *counters; // 6 x u64, zrt_counters order
+    unsigned long long *stats;    // non-NULL selects the instrumented kernel: 4 x u64 event counts
     uint32_t *hit_id;             // primary-hit kernel
     float *hit_t;
     DevSphere inl[MAX_INLINE_SPHERES]; // spheres-only scenes: operands straight from the constant bank

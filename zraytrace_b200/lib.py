@@ -41,6 +41,7 @@ def lib():
         L.zrt_scene_bvh_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.zrt_scene_launch_count.argtypes = [C.c_void_p]
         L.zrt_scene_launch_count.restype = C.c_uint64
+        L.zrt_trace_statistics.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), P(A.TraceStats)]
         L.zrt_selftest.argtypes = [C.c_int, P(C.c_uint64)]
         L.zrt_measure_peaks.argtypes = [C.c_int, P(C.c_double), C.c_int]
         _lib = L
@@ -100,6 +101,12 @@ class Scene:
         t = np.empty((params.height, params.width), np.float32)
         _check(lib().zrt_primary_hits(self._h, C.byref(camera), C.byref(params), jitter, ids.ctypes.data, t.ctypes.data))
         return ids, t
+
+    def trace_statistics(self, camera, params):
+        """Event counts (node visits, primitive tests, ...) of one render, from the instrumented kernel."""
+        st = A.TraceStats()
+        _check(lib().zrt_trace_statistics(self._h, C.byref(camera), C.byref(params), C.byref(st)))
+        return st
 
     def launch_count(self):
         return int(lib().zrt_scene_launch_count(self._h))
