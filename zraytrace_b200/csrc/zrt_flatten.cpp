@@ -12,9 +12,11 @@
 //    primitives with a binned surface-area heuristic; slots keep the reference order, so the hits
 //    are the same and only the number of node fetches changes.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 #include "zrt_internal.h"
 
@@ -53,11 +55,18 @@ struct RefTree {
     const HostScene &sc;
     std::vector<Box> sbox;            // per surface: aabb min/max
     std::vector<float> smid[3];       // per surface: aabb midpoint (the sort key, bvh.zig:38-48)
-    std::vector<RefNode> nodes;
-    uint32_t max_depth = 0;
+    std::vector<RefNode> nodes;             // preallocated (< 2n nodes); slots handed out atomically
+    std::atomic<uint32_t> n_nodes{0};
+    std::atomic<uint32_t> max_depth{0};
+    // The two halves of a split are independent (disjoint sub-ranges of the id array, nodes allocated
+    // atomically), so the top levels of the recursion fan out over host threads.  The tree is the same
+    // tree; only the node numbering (never observable) depends on timing.
+    static constexpr uint32_t kParallelDepth = 4;
+    static constexpr size_t kParallelMin = 8192;
 
     explicit RefTree(const HostScene &s) : sc(s) {
         const size_t n = sc.surfaces.size();
+        nodes.resize(2 * n + 2);
         sbox.resize(n);
         for (auto &m : smid) m.resize(n);
         for (size_t i = 0; i < n; i++) {
@@ -89,9 +98,33 @@ struct RefTree {
         for (size_t i = 0; i < n; i++) b = boxUnion(b, sbox[ids[i]]);
         return b;
     }
-    void sortAxis(int axis, uint32_t *ids, size_t n) const { // bvh.zig:71-72, std.sort.sort is stable
+    // bvh.zig:71-72: std.sort.sort is a stable comparison sort on `a.midpoint < b.midpoint`.  Small ranges use
+    // std::stable_sort; large ones an LSD radix sort on the order-preserving integer image of the float key, which
+    // is stable too and therefore yields the same permutation (-0.0 is folded onto +0.0 first, because the
+    // comparison treats them as equal; midpoints are never NaN).
+    void sortAxis(int axis, uint32_t *ids, size_t n) const {
         const float *key = smid[axis].data();
-        std::stable_sort(ids, ids + n, [key](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+        if (n < 4096) {
+            std::stable_sort(ids, ids + n, [key](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+            return;
+        }
+        std::vector<uint64_t> a(n), b(n); // (sortable key << 32) | id
+        for (size_t i = 0; i < n; i++) {
+            uint32_t u;
+            const float k = key[ids[i]] + 0.0f; // -0.0 + 0.0 = +0.0
+            std::memcpy(&u, &k, 4);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            a[i] = ((uint64_t)u << 32) | ids[i];
+        }
+        for (int pass = 0; pass < 4; pass++) {
+            size_t count[257] = {0};
+            const int shift = 32 + 8 * pass;
+            for (size_t i = 0; i < n; i++) count[((a[i] >> shift) & 0xff) + 1]++;
+            for (int k = 0; k < 256; k++) count[k + 1] += count[k];
+            for (size_t i = 0; i < n; i++) b[count[(a[i] >> shift) & 0xff]++] = a[i];
+            a.swap(b);
+        }
+        for (size_t i = 0; i < n; i++) ids[i] = (uint32_t)a[i];
     }
     // bvh.zig:85-120.  The reference re-sorts before each of the three candidate splits of an axis;
     // the 2nd and 3rd sort of an already sorted range by the same key with a stable sort change
@@ -135,16 +168,25 @@ struct RefTree {
     }
     const Box &childBox(int32_t c) const { return c >= 0 ? nodes[c].box : sbox[~c]; }
     int32_t create(int32_t left, int32_t right) { // bvh.zig:162-169
-        nodes.push_back(RefNode{boxUnion(childBox(left), childBox(right)), left, right});
-        return (int32_t)nodes.size() - 1;
+        const uint32_t i = n_nodes.fetch_add(1);
+        nodes[i] = RefNode{boxUnion(childBox(left), childBox(right)), left, right};
+        return (int32_t)i;
     }
     int32_t divide(uint32_t *ids, size_t n, uint32_t depth) { // bvh.zig:129-160
-        if (depth > max_depth) max_depth = depth;
+        uint32_t seen = max_depth.load();
+        while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
         if (n == 1) return create(~(int32_t)ids[0], ~(int32_t)ids[0]);
         if (n == 2) return create(~(int32_t)ids[1], ~(int32_t)ids[0]);
         const size_t split = optimalAxisDivide(ids, n);
-        const int32_t l = divide(ids, split, depth + 1);
-        const int32_t r = divide(ids + split, n - split, depth + 1);
+        int32_t l, r;
+        if (depth <= kParallelDepth && n >= kParallelMin) {
+            std::thread left([&] { l = divide(ids, split, depth + 1); });
+            r = divide(ids + split, n - split, depth + 1);
+            left.join();
+        } else {
+            l = divide(ids, split, depth + 1);
+            r = divide(ids + split, n - split, depth + 1);
+        }
         return create(l, r);
     }
 };
@@ -222,8 +264,9 @@ struct Flattener {
 struct SahBuilder {
     const std::vector<Box> &pbox; // per primitive
     const std::vector<uint32_t> &pref; // per primitive leaf ref
-    std::vector<DevNode> *nodes;
-    uint32_t max_depth = 0;
+    std::vector<DevNode> *nodes;  // preallocated; build() hands slots out atomically, renumber() restores pre-order
+    std::atomic<uint32_t> n_nodes{0};
+    std::atomic<uint32_t> max_depth{0};
     std::vector<float> cen[3];
 
     static float area(const Box &b) {
@@ -232,7 +275,8 @@ struct SahBuilder {
     }
     Emitted build(uint32_t *ids, size_t n, uint32_t depth) {
         if (n == 1) return Emitted{pref[ids[0]], pbox[ids[0]]};
-        if (depth > max_depth) max_depth = depth;
+        uint32_t seen = max_depth.load();
+        while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
         Box bounds = boxEmpty(), cb = boxEmpty();
         for (size_t i = 0; i < n; i++) {
             bounds = boxUnion(bounds, pbox[ids[i]]);
@@ -291,15 +335,33 @@ struct SahBuilder {
             mid = (size_t)(m - ids);
             if (mid == 0 || mid == n) mid = n / 2;
         }
-        const uint32_t my = (uint32_t)nodes->size();
-        nodes->emplace_back();
-        const Emitted l = build(ids, mid, depth + 1);
-        const Emitted r = build(ids + mid, n - mid, depth + 1);
+        const uint32_t my = n_nodes.fetch_add(1);
+        Emitted l, r;
+        if (depth <= RefTree::kParallelDepth && n >= RefTree::kParallelMin) {
+            std::thread left([&] { l = build(ids, mid, depth + 1); });
+            r = build(ids + mid, n - mid, depth + 1);
+            left.join();
+        } else {
+            l = build(ids, mid, depth + 1);
+            r = build(ids + mid, n - mid, depth + 1);
+        }
         DevNode &d = (*nodes)[my];
         d.set_box(0, l.box.mn, l.box.mx);
         d.set_box(1, r.box.mn, r.box.mx);
         d.left = l.ref; d.right = r.ref; d.pad0 = d.pad1 = 0;
         return Emitted{my, boxUnion(l.box, r.box)};
+    }
+    // DFS pre-order renumbering (parent before its subtrees, left subtree contiguous): memory locality of the
+    // traversal, and a node order that does not depend on thread timing
+    uint32_t renumber(uint32_t ref, const std::vector<DevNode> &src, std::vector<DevNode> *dst) const {
+        if (ref & REF_LEAF) return ref;
+        const uint32_t my = (uint32_t)dst->size();
+        dst->push_back(src[ref]);
+        const uint32_t l = renumber(src[ref].left, src, dst);
+        const uint32_t r = renumber(src[ref].right, src, dst);
+        (*dst)[my].left = l;
+        (*dst)[my].right = r;
+        return my;
     }
 };
 
@@ -313,11 +375,11 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
     std::vector<uint32_t> ids(n);
     for (size_t i = 0; i < n; i++) ids[i] = (uint32_t)i;
     const int32_t root = rt.divide(ids.data(), n, 1); // bvh.zig:171-185
-    out->ref_nodes = (uint32_t)rt.nodes.size();
-    out->ref_max_depth = rt.max_depth;
+    out->ref_nodes = rt.n_nodes.load();
+    out->ref_max_depth = rt.max_depth.load();
 
     Flattener fl{scene, rt, out, std::vector<uint32_t>(n, UINT32_MAX), std::vector<uint32_t>(n, 0),
-                 std::vector<int8_t>(rt.nodes.size(), -1)};
+                 std::vector<int8_t>(rt.n_nodes.load(), -1)};
     uint32_t nsph = 0;
     for (size_t i = 0; i < n; i++)
         if (scene.surfaces[i].kind == ZRT_SURFACE_SPHERE) fl.sphere_seq[i] = nsph++;
@@ -337,16 +399,19 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
             pref.push_back(scene.surfaces[surf].kind == ZRT_SURFACE_SPHERE ? (REF_LEAF | REF_SPHERE | fl.sphere_seq[surf])
                                                                            : (REF_LEAF | (uint32_t)s));
         }
-        out->nodes.clear();
-        SahBuilder sb{pbox, pref, &out->nodes};
+        std::vector<DevNode> scratch(pbox.size() + 1);
+        SahBuilder sb{pbox, pref, &scratch};
         for (int k = 0; k < 3; k++) {
             sb.cen[k].resize(pbox.size());
             for (size_t i = 0; i < pbox.size(); i++) sb.cen[k][i] = 0.5f * (pbox[i].mn[k] + pbox[i].mx[k]);
         }
         std::vector<uint32_t> pid(pbox.size());
         for (size_t i = 0; i < pid.size(); i++) pid[i] = (uint32_t)i;
-        out->root = sb.build(pid.data(), pid.size(), 1).ref;
-        out->max_depth = sb.max_depth;
+        const uint32_t root_ref = sb.build(pid.data(), pid.size(), 1).ref;
+        out->nodes.clear();
+        out->nodes.reserve(sb.n_nodes.load());
+        out->root = sb.renumber(root_ref, scratch, &out->nodes);
+        out->max_depth = sb.max_depth.load();
     }
 }
 
