@@ -164,6 +164,13 @@ void zrt_scene_destroy(zrt_scene *scene);
 int zrt_render(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
                float *out_rgb, zrt_counters *counters, zrt_timing *timing);
 
+/* raytrace.render() + the quantisation of png_image.writeFile (png_image.zig:131-142) fused on the device:
+ * out_rgb8 is width*height*3 bytes, u8 = clamp(255.999 * c, 0, 255) truncated, row 0 = TOP scanline (the order
+ * a PNG stores).  Moves a quarter of the bytes of zrt_render back to the host; the bytes are identical to
+ * quantising zrt_render's float image on the host. */
+int zrt_render_rgb8(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
+                    uint8_t *out_rgb8, zrt_counters *counters, zrt_timing *timing);
+
 /* Same work, but results stay on the device: d_rgb (width*height*3 floats) and d_counters (6 u64)
  * are DEVICE pointers on the scene's device, `stream` is a cudaStream_t (NULL = default stream).
  * Asynchronous: returns after the launches are enqueued.  This is what the multi-GPU driver uses so

@@ -30,6 +30,9 @@ int zrt_host_png_read(const char *path, uint8_t **pixels, uint32_t *width, uint3
  * gamma, image row 0 (bottom) written last. */
 int zrt_host_png_write(const char *path, const float *rgb, uint32_t width, uint32_t height);
 
+/* Same file format, from the 8-bit top-down image zrt_render_rgb8 returns (no further arithmetic). */
+int zrt_host_png_write_rgb8(const char *path, const uint8_t *rgb8_top_down, uint32_t width, uint32_t height);
+
 void zrt_host_free(void *p);
 
 /* The reference's scene builders (scenes.zig:26-277), by the CLI's scene index:

@@ -237,3 +237,22 @@ def test_exact_division_fast_paths_selftest():
     """The kernels replace `a / b` by a shared IEEE reciprocal + FMA residual corrections; the quotients must be
     the correctly rounded ones, bit for bit (exhaustive over raytrace.zig:173 numerators for ten widths)."""
     assert Z.selftest(0) == 0
+
+
+def test_device_output_stage_matches_host_quantisation(built, tmp_path):
+    """zrt_render_rgb8 fuses png_image.zig:131-142 (255.999*c, clamp, truncate, row flip) into the resolve
+    kernel: its bytes must equal the host quantisation of zrt_render's float image, and the PNG written from
+    them must equal the PNG the float path writes."""
+    from zraytrace_b200 import host
+    sc, cam, dev = built("three_balls")
+    for chunks in (0, 1):
+        p = A.make_params(96, 64, 16, 30, x_limit=A.ZRT_XLIMIT_WIDTH, sample_chunks=chunks)
+        img_f, c_f, _ = dev.render(cam, p)
+        img_8, c_8, tm = dev.render_rgb8(cam, p)
+        assert c_f.as_dict() == c_8.as_dict()
+        q = np.array([zro_py.lib().zro_quantize(float(v)) for v in img_f.ravel()], np.uint8).reshape(img_f.shape)[::-1]
+        assert np.array_equal(img_8, q)
+    a, b = str(tmp_path / "a.png"), str(tmp_path / "b.png")
+    host.png_write(a, img_f)
+    host.png_write_rgb8(b, img_8)
+    assert np.array_equal(np.array(Image.open(a)), np.array(Image.open(b)))

@@ -102,6 +102,8 @@ extern "C" int zrt_host_png_read(const char *path, uint8_t **pixels, uint32_t *w
     return ZRT_OK;
 }
 
+static int writePngRaw(const char *path, const std::vector<uint8_t> &raw, uint32_t width, uint32_t height);
+
 extern "C" int zrt_host_png_write(const char *path, const float *rgb, uint32_t width, uint32_t height) {
     if (!path || !rgb || width == 0 || height == 0) return ZRT_ERR_INVALID;
     const size_t stride = (size_t)width * 3;
@@ -113,10 +115,25 @@ extern "C" int zrt_host_png_write(const char *path, const float *rgb, uint32_t w
         for (size_t i = 0; i < stride; i++) {
             float v = 255.999f * src[i]; // png_image.zig:136-140
             v = v < 255.0f ? v : 255.0f;
-            v = v > 0.0f ? v : 0.0f;
+            v = 0.0f > v ? 0.0f : v;
             line[1 + i] = (uint8_t)v;
         }
     }
+    return writePngRaw(path, raw, width, height);
+}
+
+extern "C" int zrt_host_png_write_rgb8(const char *path, const uint8_t *rgb8, uint32_t width, uint32_t height) {
+    if (!path || !rgb8 || width == 0 || height == 0) return ZRT_ERR_INVALID;
+    const size_t stride = (size_t)width * 3;
+    std::vector<uint8_t> raw((stride + 1) * height);
+    for (uint32_t y = 0; y < height; y++) {
+        raw[(stride + 1) * y] = 0; // filter none
+        std::memcpy(&raw[(stride + 1) * y + 1], rgb8 + stride * y, stride);
+    }
+    return writePngRaw(path, raw, width, height);
+}
+
+static int writePngRaw(const char *path, const std::vector<uint8_t> &raw, uint32_t width, uint32_t height) {
     uLongf zlen = compressBound((uLong)raw.size());
     std::vector<uint8_t> z(zlen);
     if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return ZRT_ERR_IO;

@@ -19,6 +19,8 @@ namespace zrt {
 void launch_trace(const KParams &P, int mode, cudaStream_t st);
 void launch_primary(const KParams &P, int mode, cudaStream_t st);
 void launch_resolve(const float *part, float *out, uint32_t n, uint32_t chunks, float scale, cudaStream_t st);
+void launch_resolve_rgb8(const float *part, uint8_t *out, uint32_t width, uint32_t height, uint32_t chunks, float scale,
+                         cudaStream_t st);
 void launch_selftest_div(unsigned long long *mismatch, uint32_t width, uint32_t seed, cudaStream_t st);
 void launch_peak_fp32(float *out, int blocks, int threads, int iters, cudaStream_t st);
 void launch_peak_ffma(float *out, int blocks, int threads, int iters, cudaStream_t st);
@@ -124,6 +126,7 @@ struct zrt_scene {
     bool host_bvh_ready[2] = {false, false};
     // scratch owned by the scene
     DevBuf<float> part, image;
+    DevBuf<uint8_t> image8;
     DevBuf<unsigned long long> counters;
     DevBuf<uint32_t> hit_id, work;
     DevBuf<float> hit_t;
@@ -371,7 +374,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
 
 // enqueue everything for one render on `st`; d_rgb receives the final image
 int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d_counters, cudaStream_t st,
-                  cudaEvent_t e_k0, cudaEvent_t e_k1, cudaEvent_t e_r1, uint32_t *launches) {
+                  cudaEvent_t e_k0, cudaEvent_t e_k1, cudaEvent_t e_r1, uint32_t *launches, uint8_t *d_rgb8 = nullptr) {
     KParams &P = plan.P;
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 6 * sizeof(unsigned long long), st));
     float *trace_out = d_rgb;
@@ -403,7 +406,11 @@ int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d
         CUDA_TRY(cudaStreamSynchronize(st)); // `c` lives on this stack frame
     }
     if (e_k1) CUDA_TRY(cudaEventRecord(e_k1, st));
-    if (traced && P.lanes > 1) {
+    if (d_rgb8) { // fused output stage: chunk sum + 1/spp + 8-bit quantisation + row flip in one pass
+        if (traced) launch_resolve_rgb8(trace_out, d_rgb8, P.width, P.height, P.lanes, P.lanes > 1 ? P.color_scale : 1.0f, st);
+        else launch_resolve_rgb8(d_rgb, d_rgb8, P.width, P.height, 1, 1.0f, st);
+        (*launches)++;
+    } else if (traced && P.lanes > 1) {
         launch_resolve(sc->part.p, d_rgb, (uint32_t)plan.n_floats, P.lanes, P.color_scale, st);
         (*launches)++;
     }
@@ -494,7 +501,7 @@ void zrt_scene_destroy(zrt_scene *sc) {
         cudaSetDevice(sc->device);
         if (sc->stream) cudaStreamSynchronize(sc->stream);
         sc->rep_list.release(); sc->rep_bvh.release(); sc->rep_sah.release();
-        sc->mats.release(); sc->part.release(); sc->image.release(); sc->counters.release();
+        sc->mats.release(); sc->part.release(); sc->image.release(); sc->image8.release(); sc->counters.release();
         sc->hit_id.release(); sc->hit_t.release(); sc->work.release();
         for (auto &t : sc->d_texels) t.release();
         for (auto &e : sc->ev)
@@ -524,6 +531,56 @@ int zrt_render(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params
     rc = enqueueRender(sc, plan, sc->image.p, sc->counters.p, sc->stream, sc->ev[0], sc->ev[1], sc->ev[2], &launches);
     if (rc != ZRT_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_rgb, sc->image.p, plan.n_floats * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    unsigned long long h_counters[6];
+    CUDA_TRY(cudaMemcpyAsync(h_counters, sc->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaEventRecord(sc->ev[3], sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    if (counters) {
+        counters->recursion_depth_hits = h_counters[0];
+        counters->reflections = h_counters[1];
+        counters->background_hits = h_counters[2];
+        counters->pixels_processed = h_counters[3];
+        counters->samples_processed = h_counters[4];
+        counters->rays_processed = h_counters[5];
+    }
+    if (timing) {
+        float k = 0, r = 0, tot = 0;
+        cudaEventElapsedTime(&k, sc->ev[0], sc->ev[1]);
+        cudaEventElapsedTime(&r, sc->ev[1], sc->ev[2]);
+        cudaEventElapsedTime(&tot, sc->ev[0], sc->ev[3]);
+        timing->prepare_ms = prep_now;
+        timing->kernel_ms = k;
+        timing->resolve_ms = r;
+        timing->total_ms = tot;
+        timing->launches = launches;
+        timing->bvh_nodes = (uint32_t)rep->info.nodes.size();
+    }
+    return ZRT_OK;
+}
+
+int zrt_render_rgb8(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, uint8_t *out_rgb8,
+                    zrt_counters *counters, zrt_timing *timing) {
+    int rc = requireDevice(sc);
+    if (rc != ZRT_OK) return rc;
+    if (!out_rgb8) return fail(ZRT_ERR_INVALID, "out_rgb8 is NULL");
+    if (!params) return fail(ZRT_ERR_INVALID, "params is NULL");
+    if (params->flags & ZRT_FLAG_RAW_SUM) return fail(ZRT_ERR_INVALID, "ZRT_FLAG_RAW_SUM has no 8-bit form");
+    DevRep *rep = nullptr;
+    const auto t_prep0 = std::chrono::steady_clock::now();
+    rc = selectRep(sc, params, &rep);
+    if (rc != ZRT_OK) return rc;
+    const float prep_now = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_prep0).count();
+    Plan plan;
+    rc = makePlan(sc, camera, params, rep, &plan);
+    if (rc != ZRT_OK) return rc;
+    CUDA_TRY(sc->image.reserve(plan.n_floats));
+    CUDA_TRY(sc->image8.reserve(plan.n_floats));
+    CUDA_TRY(sc->counters.reserve(10));
+    uint32_t launches = 0;
+    rc = enqueueRender(sc, plan, sc->image.p, sc->counters.p, sc->stream, sc->ev[0], sc->ev[1], sc->ev[2], &launches,
+                       sc->image8.p);
+    if (rc != ZRT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_rgb8, sc->image8.p, plan.n_floats, cudaMemcpyDeviceToHost, sc->stream));
     unsigned long long h_counters[6];
     CUDA_TRY(cudaMemcpyAsync(h_counters, sc->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, sc->stream));
     CUDA_TRY(cudaEventRecord(sc->ev[3], sc->stream));

@@ -26,6 +26,7 @@ def _L():
         L.zrt_host_read_obj.argtypes = [C.c_char_p, C.c_uint32, P(P(A.Triangle)), P(C.c_uint32)]
         L.zrt_host_png_read.argtypes = [C.c_char_p, P(P(C.c_uint8)), P(C.c_uint32), P(C.c_uint32), P(C.c_uint32)]
         L.zrt_host_png_write.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.zrt_host_png_write_rgb8.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.zrt_host_free.argtypes = [C.c_void_p]
         L.zrt_host_free.restype = None
         L.zrt_host_scene_load.argtypes = [C.c_uint32, C.c_char_p, C.c_uint32, C.c_float, P(C.c_void_p)]
@@ -76,6 +77,12 @@ def png_write(path, image):
     """png_image.writeFile (png_image.zig:96-148): image float32 [H][W][3], row 0 = bottom"""
     img = np.ascontiguousarray(image, np.float32)
     _check(_L().zrt_host_png_write(path.encode(), img.ctypes.data, img.shape[1], img.shape[0]), f"png_write {path}")
+
+
+def png_write_rgb8(path, image8_top_down):
+    """8-bit top-down image (Scene.render_rgb8) -> PNG, no arithmetic"""
+    img = np.ascontiguousarray(image8_top_down, np.uint8)
+    _check(_L().zrt_host_png_write_rgb8(path.encode(), img.ctypes.data, img.shape[1], img.shape[0]), f"png_write_rgb8 {path}")
 
 
 class HostScene:

@@ -35,6 +35,7 @@ def lib():
         L.zrt_scene_destroy.argtypes = [C.c_void_p]
         L.zrt_scene_destroy.restype = None
         L.zrt_render.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_void_p, P(A.Counters), P(A.Timing)]
+        L.zrt_render_rgb8.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_void_p, P(A.Counters), P(A.Timing)]
         L.zrt_render_device.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_void_p, C.c_void_p, C.c_void_p]
         L.zrt_primary_hits.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_int, C.c_void_p, C.c_void_p]
         L.zrt_scene_bvh_info.argtypes = [C.c_void_p, C.c_uint32, P(A.BvhInfo)]
@@ -89,6 +90,14 @@ class Scene:
         img = np.empty((params.height, params.width, 3), np.float32)
         cnt, tm = A.Counters(), A.Timing()
         _check(lib().zrt_render(self._h, C.byref(camera), C.byref(params), img.ctypes.data, C.byref(cnt), C.byref(tm)))
+        return img, cnt, tm
+
+    def render_rgb8(self, camera, params):
+        """-> (uint8 [H][W][3] with row 0 = TOP scanline, quantised on the device like png_image.zig:136-140,
+        Counters, Timing)"""
+        img = np.empty((params.height, params.width, 3), np.uint8)
+        cnt, tm = A.Counters(), A.Timing()
+        _check(lib().zrt_render_rgb8(self._h, C.byref(camera), C.byref(params), img.ctypes.data, C.byref(cnt), C.byref(tm)))
         return img, cnt, tm
 
     def render_device(self, camera, params, d_rgb_ptr, d_counters_ptr, stream_ptr=0):
