@@ -357,6 +357,9 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     if (lanes < 1u) lanes = 1u;
     if (pixels * lanes > 0xFFFFFF00ull) return fail(ZRT_ERR_INVALID, "image too large");
     P.lanes = lanes;
+    P.lanes_log2 = 0;
+    while ((1u << P.lanes_log2) < lanes) P.lanes_log2++;
+    P.x_end_magic = P.x_end > 1 ? (uint32_t)((0x100000000ull + P.x_end - 1) / P.x_end) : 0u;
     P.max_depth = p->max_depth;
     P.seed32 = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
     P.color_scale = (p->flags & ZRT_FLAG_RAW_SUM) ? 1.0f : 1.0f / (float)p->samples_per_pixel; // raytrace.zig:157
@@ -366,7 +369,16 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.triA = r->triA.p; P.triE1 = r->triE1.p; P.triE2 = r->triE2.p; P.triMeta = r->triMeta.p;
     P.list = r->list.p; P.nodes = r->nodes.p; P.mats = sc->mats.p;
     if (r->mode == MODE_SPHERES)
-        for (uint32_t i = 0; i < r->n_spheres; i++) P.inl[i] = r->h_spheres[i];
+        for (uint32_t i = 0; i < MAX_INLINE_SPHERES; i++) {
+            KParams::SpherePair &pr = P.inl[i / 2];
+            if (i < r->n_spheres) {
+                const DevSphere &sp = r->h_spheres[i];
+                pr.ncx[i & 1] = -sp.cx; pr.ncy[i & 1] = -sp.cy; pr.ncz[i & 1] = -sp.cz; pr.nr2[i & 1] = -sp.r2;
+            } else {
+                pr.ncx[i & 1] = pr.ncy[i & 1] = pr.ncz[i & 1] = 0.0f;
+                pr.nr2[i & 1] = 1e30f; // c = |oc|^2 + 1e30 > half_b^2: the discriminant is always negative
+            }
+        }
     plan->mode = r->mode;
     plan->n_floats = (size_t)p->width * p->height * 3;
     return ZRT_OK;

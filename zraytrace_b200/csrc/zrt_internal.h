@@ -95,6 +95,8 @@ struct KParams {
     uint32_t width, height, x_end;
     uint32_t s_begin, s_end; // global sample range of this launch
     uint32_t lanes;   // L: slices per pixel (power of two <= 32); a work item is (pixel, slice)
+    uint32_t lanes_log2;
+    uint32_t x_end_magic; // ceil(2^32 / x_end) (0 if x_end == 1): q / x_end ~ umulhi(q, magic), corrected by one
     uint32_t *work_counter; // global item queue head, zeroed before the launch
     uint32_t max_depth, seed32;
     float color_scale; // 1/spp, or 1 for ZRT_FLAG_RAW_SUM
@@ -115,7 +117,12 @@ struct KParams {
     unsigned long long *stats;    // non-NULL selects the instrumented kernel: 4 x u64 event counts
     uint32_t *hit_id;             // primary-hit kernel
     float *hit_t;
-    DevSphere inl[MAX_INLINE_SPHERES]; // spheres-only scenes: operands straight from the constant bank
+    // spheres-only scenes: operands straight from the constant bank, two spheres per packed f32x2 operand.
+    // pair p holds spheres 2p and 2p+1: negated centre coordinates and negated r^2 (a - b == a + (-b) exactly);
+    // an odd count is padded with a sphere that can never be hit (r^2 = -1e30)
+    struct SpherePair {
+        float ncx[2], ncy[2], ncz[2], nr2[2];
+    } inl[MAX_INLINE_SPHERES / 2];
 };
 
 enum TraceMode { MODE_SPHERES = 0, MODE_LIST = 1, MODE_BVH = 2 };
