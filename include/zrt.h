@@ -118,10 +118,14 @@ typedef struct zrt_params {
 enum {
     ZRT_FLAG_RAW_SUM = 1u << 0, /* output the un-normalised sum over the traced samples (for multi-GPU
                                    reduction) instead of sum * (1/samples_per_pixel) raytrace.zig:157,182 */
-    ZRT_FLAG_BVH_REFERENCE = 1u << 1 /* traverse the flattened topology of the reference's own tree
+    ZRT_FLAG_BVH_REFERENCE = 1u << 1, /* traverse the flattened topology of the reference's own tree
                                    (bvh.zig:62-185) instead of the binned-SAH tree libzrt builds by default over
                                    the same primitives; hits are identical either way (ties break on the
                                    reference DFS order, unreachable surfaces are pruned), only speed differs */
+    ZRT_FLAG_KERNEL_THREAD = 1u << 2, /* the one-thread-per-path megakernel k_trace (the default; wins over SORTED) */
+    ZRT_FLAG_KERNEL_SORTED = 1u << 3  /* the block-sorted-shading kernel k_trace_sorted (shared-memory wavefront
+                                   inside a thread block).  Images and counters are bit-identical between the
+                                   two kernels, only speed differs; the thread kernel measured faster */
 };
 
 /* raytrace.zig:20-34 Progress (the six u64 counters), same semantics */

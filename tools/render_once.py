@@ -18,17 +18,19 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--reftree", action="store_true")
 ap.add_argument("--chunks", type=int, default=0)
 ap.add_argument("--primary", action="store_true")
+ap.add_argument("--kernel", default="auto", choices=["auto", "thread", "sorted"])
 a = ap.parse_args()
 wl = dict(bench.WORKLOADS[a.workload])
 if a.spp:
     wl["spp"] = a.spp
 hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0))
-p = bench.params_for(wl, flags=A.ZRT_FLAG_BVH_REFERENCE if a.reftree else 0, sample_chunks=a.chunks)
+kflag = {"auto": 0, "thread": A.ZRT_FLAG_KERNEL_THREAD, "sorted": A.ZRT_FLAG_KERNEL_SORTED}[a.kernel]
+p = bench.params_for(wl, flags=(A.ZRT_FLAG_BVH_REFERENCE if a.reftree else 0) | kflag, sample_chunks=a.chunks)
 with Z.Scene(hs, device=0) as sc:
     for i in range(a.reps):
         if a.primary:
             sc.primary_hits(hs.camera, p)
         img, c, t = sc.render(hs.camera, p)
-        print(json.dumps({"rep": i, "workload": a.workload, "spp": wl["spp"], "kernel_ms": t.kernel_ms, "total_ms": t.total_ms,
+        print(json.dumps({"rep": i, "kernel": a.kernel, "workload": a.workload, "spp": wl["spp"], "kernel_ms": t.kernel_ms, "total_ms": t.total_ms,
                           "prepare_ms": t.prepare_ms, "launches": t.launches, "bvh_nodes": t.bvh_nodes,
                           "Mrays_s_kernel": c.rays_processed / t.kernel_ms / 1e3, **c.as_dict()}))

@@ -379,6 +379,14 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
                 pr.nr2[i & 1] = 1e30f; // c = |oc|^2 + 1e30 > half_b^2: the discriminant is always negative
             }
         }
+    // kernel choice: the one-thread-per-path megakernel measured faster on every workload (C5: 43.2 ms against
+    // 55.9 ms, DESIGN.md "Megakernel vs wavefront"), so block-sorted shading is opt-in.  It packs (px, py) into
+    // 16 bits each and the material index into 18 bits.
+    const bool sorted_ok = p->width < 65536u && p->height < 65536u && sc->host.materials.size() < (1u << 18);
+    if ((p->flags & ZRT_FLAG_KERNEL_SORTED) && !sorted_ok)
+        return fail(ZRT_ERR_INVALID, "ZRT_FLAG_KERNEL_SORTED needs width, height < 65536 and < 262144 materials");
+    const bool sorted = (p->flags & ZRT_FLAG_KERNEL_SORTED) && !(p->flags & ZRT_FLAG_KERNEL_THREAD);
+    P.sorted_shading = (sorted && sorted_ok) ? 1u : 0u;
     plan->mode = r->mode;
     plan->n_floats = (size_t)p->width * p->height * 3;
     return ZRT_OK;

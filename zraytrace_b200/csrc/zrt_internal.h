@@ -102,6 +102,7 @@ struct KParams {
     float color_scale; // 1/spp, or 1 for ZRT_FLAG_RAW_SUM
     uint32_t count_pixels; // 1 if this launch owns sample 0 (pixels_processed is counted once)
     uint32_t jitter;       // primary-hit kernel only
+    uint32_t sorted_shading; // 1: k_trace_sorted (block-sorted shading), 0: k_trace (one thread per path)
     // scene
     uint32_t n_spheres, n_list;
     uint32_t root; // BVH root ref
