@@ -123,6 +123,7 @@ enum {
                                    the same primitives; hits are identical either way (ties break on the
                                    reference DFS order, unreachable surfaces are pruned), only speed differs */
     ZRT_FLAG_KERNEL_THREAD = 1u << 2, /* the one-thread-per-path megakernel k_trace (the default; wins over SORTED) */
+    ZRT_FLAG_KERNEL_WARP = 1u << 4,   /* BVH scenes: the warp-scheduled state machine k_trace_ws (opt-in; ties or loses) */
     ZRT_FLAG_KERNEL_SORTED = 1u << 3  /* the block-sorted-shading kernel k_trace_sorted (shared-memory wavefront
                                    inside a thread block).  Images and counters are bit-identical between the
                                    two kernels, only speed differs; the thread kernel measured faster */

@@ -122,25 +122,26 @@ def test_sorted_and_thread_kernels_are_bit_identical(built, name, w, spp, depth,
     is unchanged, so image bits and counters must be equal, and both must match the oracle."""
     sc, cam, dev = built(name)
     pt = A.make_params(w, w, spp, depth, sample_chunks=chunks, flags=A.ZRT_FLAG_KERNEL_THREAD)
-    ps = A.make_params(w, w, spp, depth, sample_chunks=chunks, flags=A.ZRT_FLAG_KERNEL_SORTED)
     img_t, c_t, _ = dev.render(cam, pt)
-    img_s, c_s, _ = dev.render(cam, ps)
-    _counters_equal(c_t, c_s)
-    assert np.array_equal(img_t.view(np.uint32), img_s.view(np.uint32))
     img_o, c_o, _ = zro_py.render(sc, cam, pt, rng=zro_py.RNG_CTR, math=zro_py.MATH_SPEC)
-    _counters_equal(c_o, c_s)
-    np.testing.assert_allclose(img_s, img_o, rtol=2e-5, atol=1e-6)
+    for flag in (A.ZRT_FLAG_KERNEL_SORTED, A.ZRT_FLAG_KERNEL_WARP):  # WARP only differs on BVH scenes
+        ps = A.make_params(w, w, spp, depth, sample_chunks=chunks, flags=flag)
+        img_s, c_s, _ = dev.render(cam, ps)
+        _counters_equal(c_t, c_s)
+        assert np.array_equal(img_t.view(np.uint32), img_s.view(np.uint32))
+        _counters_equal(c_o, c_s)
+        np.testing.assert_allclose(img_s, img_o, rtol=2e-5, atol=1e-6)
 
 
 def test_sorted_kernel_list_mode_and_edges(built):
     sc, cam, dev = built("teapot_circle")
     for bvh in (0, 1):
         pt = A.make_params(40, 40, 4, 30, bvh=bvh, flags=A.ZRT_FLAG_KERNEL_THREAD)
-        ps = A.make_params(40, 40, 4, 30, bvh=bvh, flags=A.ZRT_FLAG_KERNEL_SORTED)
         img_t, c_t, _ = dev.render(cam, pt)
-        img_s, c_s, _ = dev.render(cam, ps)
-        _counters_equal(c_t, c_s)
-        assert np.array_equal(img_t.view(np.uint32), img_s.view(np.uint32))
+        for flag in (A.ZRT_FLAG_KERNEL_SORTED, A.ZRT_FLAG_KERNEL_WARP, A.ZRT_FLAG_KERNEL_WARP | A.ZRT_FLAG_BVH_REFERENCE):
+            img_s, c_s, _ = dev.render(cam, A.make_params(40, 40, 4, 30, bvh=bvh, flags=flag))
+            _counters_equal(c_t, c_s)
+            assert np.array_equal(img_t.view(np.uint32), img_s.view(np.uint32))
     sc, cam, dev = built("three_balls")
     for wh, spp, depth in (((1, 1), 7, 30), ((9, 5), 3, 30), ((32, 32), 2, 1), ((700, 3), 2, 30)):
         kw = dict(x_limit=A.ZRT_XLIMIT_WIDTH, sample_chunks=1)

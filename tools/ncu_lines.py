@@ -31,7 +31,7 @@ for line in dis.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);", line)
     if m:
         addr2line[int(m.group(1), 16)] = (cur, m.group(2))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + re.sub(r"ILi.*", "", kern).replace("_ZN3zrt", "")],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + re.sub(r"IL[ib].*", "", kern).replace("_ZN3zrt", "")],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")

@@ -387,6 +387,12 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         return fail(ZRT_ERR_INVALID, "ZRT_FLAG_KERNEL_SORTED needs width, height < 65536 and < 262144 materials");
     const bool sorted = (p->flags & ZRT_FLAG_KERNEL_SORTED) && !(p->flags & ZRT_FLAG_KERNEL_THREAD);
     P.sorted_shading = (sorted && sorted_ok) ? 1u : 0u;
+    // BVH scenes: the warp-scheduled state machine k_trace_ws is opt-in as well: with its best thresholds it ties with
+    // k_trace on C2/C4 (13.6 vs 13.2 ms, 120 vs 122 ms) and loses on C3 (42.8 vs 37.2 ms), DESIGN.md section 4.1
+    P.warp_scheduled = ((p->flags & ZRT_FLAG_KERNEL_WARP) && r->mode == MODE_BVH && !sorted) ? 1u : 0u;
+    P.ws_node_min = 8;   // keep stepping nodes while >= 8 lanes can
+    P.ws_leaf_min = 4;   // run postponed leaves once 4 lanes hold one
+    P.ws_shade_min = 24; // shade / regenerate once 24 lanes wait for it
     plan->mode = r->mode;
     plan->n_floats = (size_t)p->width * p->height * 3;
     return ZRT_OK;
