@@ -124,6 +124,13 @@ enum {
                                    reference DFS order, unreachable surfaces are pruned), only speed differs */
     ZRT_FLAG_KERNEL_THREAD = 1u << 2, /* the one-thread-per-path megakernel k_trace (the default; wins over SORTED) */
     ZRT_FLAG_KERNEL_WARP = 1u << 4,   /* BVH scenes: the warp-scheduled state machine k_trace_ws (opt-in; ties or loses) */
+    ZRT_FLAG_RUSSIAN_ROULETTE = 1u << 5, /* src/README.md:5-6 TODO of the reference: from the 3rd ray of a path on,
+                                   continue with probability p = clamp(max(throughput), 0.05, 1) and divide the
+                                   throughput by p.  Changes the estimator's variance, not its expectation */
+    ZRT_FLAG_SAMPLER_HALTON = 1u << 6,   /* src/README.md:8-13 TODO: pixel jitter from the Halton (2,3) sequence over
+                                   the global sample index, Cranley-Patterson rotated per pixel, instead of two
+                                   independent uniforms.  Both extensions run on k_trace only and are restated by
+                                   the oracle (draw-for-draw parity); zrt_trace_statistics ignores them */
     ZRT_FLAG_KERNEL_SORTED = 1u << 3  /* the block-sorted-shading kernel k_trace_sorted (shared-memory wavefront
                                    inside a thread block).  Images and counters are bit-identical between the
                                    two kernels, only speed differs; the thread kernel measured faster */

@@ -216,6 +216,7 @@ struct Ctx {
     int traversal;
     Stats *stats;
     int math = ZRO_MATH_SPEC;
+    bool roulette = false; // ZRT_FLAG_RUSSIAN_ROULETTE (sampler extension, see rrProbability below)
 };
 // transcendental dispatch: ZRO_MATH_SPEC = the kernels of zro_math.h, ZRO_MATH_LIBM = glibc
 inline f32 mAcos(int m, f32 x) { return m == ZRO_MATH_LIBM ? std::acos(x) : zro_math::acos(x); }
@@ -453,6 +454,11 @@ struct Rng {
         *r2 = Xoroshiro128::bitsToFloat(w[1]);
         *coin = (w[2] >> 31) != 0;
     }
+    f32 roulette(uint32_t bounce) { // sampler extension: 4th word of the scatter's draw
+        if (mode == ZRO_RNG_REF) return seq->float32();
+        uint32_t w[4]; words(bounce, w);
+        return Xoroshiro128::bitsToFloat(w[3]);
+    }
     f32 dielectric(uint32_t bounce) { // material.zig:117
         if (mode == ZRO_RNG_REF) return seq->float32();
         uint32_t w[4]; words(bounce, w);
@@ -585,8 +591,34 @@ inline bool closestHit(const Scene &sc, const Ray &ray, const Ctx &cx, HitRecord
     return any;
 }
 
+// ---- sampler extensions (the reference's TODO list src/README.md:5-13; spec in include/zrt.h and DESIGN.md) ----
+constexpr uint32_t kRouletteStart = 3;
+inline f32 rrProbability(const Color &thr) { // continuation probability: max channel, clamped to [0.05, 1]
+    f32 p = thr.r;
+    if (thr.g > p) p = thr.g;
+    if (thr.b > p) p = thr.b;
+    if (p > 1.0f) p = 1.0f;
+    if (p < 0.05f) p = 0.05f;
+    return p;
+}
+inline f32 halton2(uint32_t i) { // radical inverse base 2: bit reversal, exact in f32 after dropping 8 bits
+    uint32_t r = 0;
+    for (int b = 0; b < 32; b++) r |= ((i >> b) & 1u) << (31 - b);
+    return (f32)(r >> 8) * 5.9604644775390625e-8f;
+}
+inline f32 halton3(uint32_t i) { // digits of i in base 3, reversed, over 3^k
+    uint32_t r = 0, d = 1;
+    while (i) {
+        r = r * 3u + i % 3u;
+        d *= 3u;
+        i /= 3u;
+    }
+    return (f32)r / (f32)d;
+}
+
+// thr: product of the attenuations from the camera to this ray, front to back (only the roulette reads it)
 Color rayColor(const Scene &sc, const Ray &ray, uint32_t depth, uint32_t max_depth, zrt_counters *progress,
-               Rng &rng, const Ctx &cx) { // raytrace.zig:62-100
+               Rng &rng, const Ctx &cx, Color thr = Color{1.0f, 1.0f, 1.0f}) { // raytrace.zig:62-100
     if (depth <= 0) {
         progress->recursion_depth_hits += 1;
         return Color{0, 0, 0};
@@ -603,6 +635,17 @@ Color rayColor(const Scene &sc, const Ray &ray, uint32_t depth, uint32_t max_dep
     if (!materialScatter(sc.desc, hit.surface->material(), ray, hit, rng, bounce, cx.stats, cx.math, &sct))
         return Color{0, 0, 0};
     progress->reflections += 1;
+    if (cx.roulette) {
+        thr = cmul(thr, sct.attenuation);
+        if (bounce >= kRouletteStart) {
+            const f32 p = rrProbability(thr);
+            if (rng.roulette(bounce) >= p) return Color{0, 0, 0}; // ends here: no further ray, nothing counted
+            thr = Color{thr.r / p, thr.g / p, thr.b / p};
+            const Color c = rayColor(sc, sct.scattered_ray, depth - 1, max_depth, progress, rng, cx, thr);
+            return cmul(sct.attenuation, Color{c.r / p, c.g / p, c.b / p});
+        }
+        return cmul(sct.attenuation, rayColor(sc, sct.scattered_ray, depth - 1, max_depth, progress, rng, cx, thr));
+    }
     return cmul(sct.attenuation, rayColor(sc, sct.scattered_ray, depth - 1, max_depth, progress, rng, cx));
 }
 
@@ -677,6 +720,8 @@ void renderRows(const Scene &sc, const zrt_camera *camera, const zrt_params *p, 
     sampleRange(p, &s_begin, &s_end);
     const uint32_t x_end = xLimit(p);
     Ctx cx{traversal, stats, math};
+    cx.roulette = (p->flags & ZRT_FLAG_RUSSIAN_ROULETTE) != 0;
+    const bool halton = (p->flags & ZRT_FLAG_SAMPLER_HALTON) != 0;
     Rng rng{rng_mode, seq};
     rng.seed32 = foldSeed(p->seed);
     for (uint32_t y = y0; y < y1; y++) { // raytrace.zig:162-187
@@ -687,7 +732,16 @@ void renderRows(const Scene &sc, const zrt_camera *camera, const zrt_params *p, 
             for (uint32_t sample = s_begin; sample < s_end; sample++) {
                 rng.sample = sample;
                 f32 xi_u, xi_v;
-                rng.jitter(&xi_u, &xi_v);
+                if (halton) { // Halton (2,3) point of the global sample index, rotated by the pixel's offsets
+                    uint32_t w[4];
+                    rngCtr(rng.pixel, 0xFFFFFFFFu, 0, rng.seed32, w);
+                    xi_u = Xoroshiro128::bitsToFloat(w[0]) + halton2(sample + 1);
+                    xi_v = Xoroshiro128::bitsToFloat(w[1]) + halton3(sample + 1);
+                    if (xi_u >= 1.0f) xi_u -= 1.0f;
+                    if (xi_v >= 1.0f) xi_v -= 1.0f;
+                } else {
+                    rng.jitter(&xi_u, &xi_v);
+                }
                 const f32 u = ((f32)x + xi_u - 0.5f) / f_width;
                 const f32 v = (f_y + xi_v - 0.5f) / f_height;
                 const Ray ray = cameraGetRay(*camera, u, v);
@@ -727,6 +781,7 @@ int zro_render(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_p
                zro_stats *stats_out) {
     if (!validate(desc) || !camera || !p || !out_rgb || p->width == 0 || p->height == 0) return ZRT_ERR_INVALID;
     if (n_threads > 1 && rng_mode != ZRO_RNG_CTR) return ZRT_ERR_INVALID;
+    if ((p->flags & ZRT_FLAG_SAMPLER_HALTON) && rng_mode != ZRO_RNG_CTR) return ZRT_ERR_INVALID; // keyed on (pixel, sample)
     if (n_threads < 1) n_threads = 1;
     Scene sc;
     buildScene(sc, desc, p->bounded_volume_hierarchy != 0);

@@ -393,6 +393,10 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.ws_node_min = 8;   // keep stepping nodes while >= 8 lanes can
     P.ws_leaf_min = 4;   // run postponed leaves once 4 lanes hold one
     P.ws_shade_min = 24; // shade / regenerate once 24 lanes wait for it
+    P.halton = (p->flags & ZRT_FLAG_SAMPLER_HALTON) ? 1u : 0u;
+    P.roulette = (p->flags & ZRT_FLAG_RUSSIAN_ROULETTE) ? 1u : 0u;
+    if ((P.halton || P.roulette) && (p->flags & (ZRT_FLAG_KERNEL_SORTED | ZRT_FLAG_KERNEL_WARP)))
+        return fail(ZRT_ERR_INVALID, "the sampler extensions run on the thread kernel only");
     plan->mode = r->mode;
     plan->n_floats = (size_t)p->width * p->height * 3;
     return ZRT_OK;

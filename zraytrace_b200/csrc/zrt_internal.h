@@ -103,6 +103,7 @@ struct KParams {
     uint32_t count_pixels; // 1 if this launch owns sample 0 (pixels_processed is counted once)
     uint32_t jitter;       // primary-hit kernel only
     uint32_t sorted_shading; // 1: k_trace_sorted (block-sorted shading), 0: k_trace (one thread per path)
+    uint32_t halton, roulette; // sampler extensions (ZRT_FLAG_SAMPLER_HALTON, ZRT_FLAG_RUSSIAN_ROULETTE): k_trace<EXT>
     uint32_t warp_scheduled; // BVH scenes: 1: k_trace_ws (warp-scheduled node / leaf / shade sections)
     uint32_t ws_node_min, ws_leaf_min, ws_shade_min; // k_trace_ws: lanes that must wait for a section before the warp runs it
     // scene
