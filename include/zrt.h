@@ -131,6 +131,7 @@ enum {
                                    the global sample index, Cranley-Patterson rotated per pixel, instead of two
                                    independent uniforms.  Both extensions run on k_trace only and are restated by
                                    the oracle (draw-for-draw parity); zrt_trace_statistics ignores them */
+    ZRT_FLAG_KERNEL_X2 = 1u << 7,     /* spheres-only scenes: k_trace_x2, two paths per thread in packed f32x2 (opt-in: ties) */
     ZRT_FLAG_KERNEL_SORTED = 1u << 3  /* the block-sorted-shading kernel k_trace_sorted (shared-memory wavefront
                                    inside a thread block).  Images and counters are bit-identical between the
                                    two kernels, only speed differs; the thread kernel measured faster */

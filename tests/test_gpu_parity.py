@@ -151,6 +151,21 @@ def test_sorted_kernel_list_mode_and_edges(built):
         assert np.array_equal(img_t.view(np.uint32), img_s.view(np.uint32))
 
 
+@pytest.mark.parametrize("w,h,spp,depth,chunks", [(160, 160, 24, 30, 0), (33, 33, 7, 30, 1), (64, 48, 9, 3, 2), (1, 1, 5, 30, 1)])
+def test_two_paths_per_thread_kernel(built, w, h, spp, depth, chunks):
+    """k_trace_x2 traces two samples of an item per thread in packed f32x2 registers: the same set of paths with the
+    same arithmetic (counters equal the oracle's), only the order of the per-item f32 sum changes."""
+    sc, cam, dev = built("three_balls")
+    kw = dict(x_limit=A.ZRT_XLIMIT_WIDTH, sample_chunks=chunks)
+    img_t, c_t, _ = dev.render(cam, A.make_params(w, h, spp, depth, flags=A.ZRT_FLAG_KERNEL_THREAD, **kw))
+    img_x, c_x, _ = dev.render(cam, A.make_params(w, h, spp, depth, flags=A.ZRT_FLAG_KERNEL_X2, **kw))
+    _counters_equal(c_t, c_x)
+    np.testing.assert_allclose(img_x, img_t, rtol=1e-5, atol=1e-6)
+    img_o, c_o, _ = zro_py.render(sc, cam, A.make_params(w, h, spp, depth, **kw), rng=zro_py.RNG_CTR, math=zro_py.MATH_SPEC)
+    _counters_equal(c_o, c_x)
+    np.testing.assert_allclose(img_x, img_o, rtol=2e-5, atol=1e-6)
+
+
 def test_reference_topology_full_paths(built):
     sc, cam, dev = built("teapot")
     p = A.make_params(64, 64, 8, 30, sample_chunks=1)

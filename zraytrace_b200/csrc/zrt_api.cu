@@ -397,6 +397,15 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.roulette = (p->flags & ZRT_FLAG_RUSSIAN_ROULETTE) ? 1u : 0u;
     if ((P.halton || P.roulette) && (p->flags & (ZRT_FLAG_KERNEL_SORTED | ZRT_FLAG_KERNEL_WARP)))
         return fail(ZRT_ERR_INVALID, "the sampler extensions run on the thread kernel only");
+    P.neg_zero[0] = P.neg_zero[1] = -0.0f;
+    if (r->mode == MODE_SPHERES)
+        for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++) {
+            const DevSphere &sp = r->h_spheres[i];
+            KParams::SphereX2 &e = P.inl2[i];
+            e.ncx[0] = e.ncx[1] = -sp.cx; e.ncy[0] = e.ncy[1] = -sp.cy; e.ncz[0] = e.ncz[1] = -sp.cz;
+            e.nr2[0] = e.nr2[1] = -sp.r2;
+        }
+    P.two_paths = (r->mode == MODE_SPHERES && (p->flags & ZRT_FLAG_KERNEL_X2) && !P.sorted_shading && !P.halton && !P.roulette) ? 1u : 0u;
     plan->mode = r->mode;
     plan->n_floats = (size_t)p->width * p->height * 3;
     return ZRT_OK;

@@ -127,6 +127,13 @@ struct KParams {
     struct SpherePair {
         float ncx[2], ncy[2], ncz[2], nr2[2];
     } inl[MAX_INLINE_SPHERES / 2];
+    // k_trace_x2 (two paths per thread): one sphere per entry, every value twice, so that an operand pair comes
+    // straight from the constant bank; neg_zero is the -0.0 pair no compiler pass can see through (see K1x2)
+    struct SphereX2 {
+        float ncx[2], ncy[2], ncz[2], nr2[2];
+    } inl2[MAX_INLINE_SPHERES];
+    float neg_zero[2];
+    uint32_t two_paths; // 1: k_trace_x2
 };
 
 enum TraceMode { MODE_SPHERES = 0, MODE_LIST = 1, MODE_BVH = 2 };
