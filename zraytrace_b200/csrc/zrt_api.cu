@@ -398,6 +398,9 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     if ((P.halton || P.roulette) && (p->flags & (ZRT_FLAG_KERNEL_SORTED | ZRT_FLAG_KERNEL_WARP)))
         return fail(ZRT_ERR_INVALID, "the sampler extensions run on the thread kernel only");
     P.neg_zero[0] = P.neg_zero[1] = -0.0f;
+    P.pk_ll[0] = P.llx; P.pk_ll[1] = P.lly; P.pk_h[0] = P.hx; P.pk_h[1] = P.hy; P.pk_v[0] = P.vx; P.pk_v[1] = P.vy;
+    P.pk_no[0] = -P.ox; P.pk_no[1] = -P.oy; P.pk_nwh[0] = -P.f_width; P.pk_nwh[1] = -P.f_height;
+    P.pk_rcp[0] = P.rcp_width; P.pk_rcp[1] = P.rcp_height;
     if (r->mode == MODE_SPHERES)
         for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++) {
             const DevSphere &sp = r->h_spheres[i];

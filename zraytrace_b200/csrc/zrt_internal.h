@@ -133,6 +133,8 @@ struct KParams {
         float ncx[2], ncy[2], ncz[2], nr2[2];
     } inl2[MAX_INLINE_SPHERES];
     float neg_zero[2];
+    // packed operands of primary_direction_raw: (x, y) pairs of the camera vectors, (width, height) and reciprocals
+    float pk_ll[2], pk_h[2], pk_v[2], pk_no[2], pk_nwh[2], pk_rcp[2];
     uint32_t two_paths; // 1: k_trace_x2
 };
 

@@ -10,7 +10,7 @@ import numpy as np
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzrt.so")
+LIB_PATH = os.environ.get("ZRT_LIB_PATH") or os.path.join(_HERE, "libzrt.so")  # override: A/B builds of the library
 _lib = None
 
 
