@@ -339,12 +339,14 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.s_begin = sb; P.s_end = se;
     plan->n_samples = se - sb;
     const uint64_t pixels = (uint64_t)P.x_end * P.height;
-    // L slices per pixel (see k_trace): 8 measured best on C5 at 125..1000 spp (items of 16..125 samples), more
-    // only when the image is so small that 8 would leave resident warps without items (~1.2 M items wanted);
-    // the caller can pin it (sample_chunks = 1 reproduces the reference's sequential f32 sum per pixel)
+    // L slices per pixel (see k_trace).  Sphere lists: 8 measured best on C5 at 125..1000 spp (items of 16..125
+    // samples), more only when the image is so small that 8 would leave resident warps without items (~1.2 M items
+    // wanted).  BVH / surface-list scenes: 32, i.e. the 32 lanes of a warp trace 32 slices of ONE pixel, so their
+    // primary rays walk the same nodes (measured against 8: C2 13.2 -> 11.0 ms, C3 36.0 -> 34.2, C4 119 -> 101).
+    // The caller can pin it (sample_chunks = 1 reproduces the reference's sequential f32 sum per pixel).
     uint32_t lanes = p->sample_chunks;
     if (lanes == 0) {
-        const uint32_t by_samples = 8u;
+        const uint32_t by_samples = (r->mode == MODE_SPHERES) ? 8u : 32u;
         const uint64_t by_items = (1200000ull + pixels - 1) / (pixels ? pixels : 1);
         lanes = (uint32_t)(by_samples > by_items ? by_samples : by_items);
         uint32_t p2 = 1;
