@@ -4,10 +4,9 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c5_v7.json 2> gpurun_out/bench_c5_v7.err; echo "bench c5 rc=$?"
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_c5_v7.json 2> gpurun_out/bench_ref_c5_v7.err; echo "bench reference rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c5_v7.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launches_v7.log 2>&1; echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_trace -c 1 -f -o gpurun_out/prof_c5_v7 python tools/render_once.py --workload c5 --reps 1 > gpurun_out/ncu_c5_v7.log 2>&1; echo "ncu full rc=$?"
-for w in c1 c2 c3; do python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/bench_${w}_v7.json 2> gpurun_out/bench_${w}_v7.err; echo "bench $w rc=$?"; done
-for ch in 8 16 32; do python tools/render_once.py --workload c1 --reps 4 --chunks $ch | tail -1 | cut -c1-110; done
-cut -c1-200 gpurun_out/bench_c5_v7.json; cut -c1-200 gpurun_out/bench_ref_c5_v7.json
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c5_v8.json 2> gpurun_out/bench_c5_v8.err; echo "bench c5 rc=$?"
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_c5_v8.json 2> gpurun_out/bench_ref_c5_v8.err; echo "bench reference rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c5_v8.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launches_v8.log 2>&1; echo "ncu launches rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_trace -c 1 -f -o gpurun_out/prof_c5_v8 python tools/render_once.py --workload c5 --reps 1 > gpurun_out/ncu_c5_v8.log 2>&1; echo "ncu full rc=$?"
+for w in c1 c2 c3 c4; do python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/bench_${w}_v8.json 2> gpurun_out/bench_${w}_v8.err; echo "bench $w rc=$?"; done
+cut -c1-200 gpurun_out/bench_c5_v8.json; cut -c1-200 gpurun_out/bench_ref_c5_v8.json
