@@ -149,7 +149,7 @@ def run_reference(args, wl_name, wl):
             "config": {"workload": f"{wl_name}: {wl['desc']}", "spp_per_step": spp},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline leg
@@ -344,12 +344,30 @@ def run_zrt(args, wl_name, wl):
                                            "parity forbids contraction); MEASURED_PEAKS.json has no FP32-issue figure",
                             "k0": peaks, "hbm_peak_gbs": peaks_file.get("hbm_gbs"), "hbm_peak_source": peaks_src,
                             "mrays_per_s_kernel_only": rays_rank / (kernel_ms * 1e-3) / 1e6}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any library prints while the
+    benchmark runs (NCCL prints its version banner on stdout) has been pointed at stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)  # C-level stdout of every library -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
