@@ -354,6 +354,8 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         lanes = p2;
     }
     if (lanes > 32u) lanes = 32u;
+    if (p->sample_chunks == 0) // the slice buffer is lanes x 12 B per pixel: keep the automatic choice under 2 GiB
+        while (lanes > 1u && (uint64_t)p->width * p->height * 12ull * lanes > (2ull << 30)) lanes >>= 1;
     while (lanes & (lanes - 1u)) lanes &= lanes - 1u;          // round down to a power of two
     while (lanes > 1u && lanes > plan->n_samples) lanes >>= 1; // every slice gets at least one sample
     if (lanes < 1u) lanes = 1u;
