@@ -13,6 +13,9 @@
 //    are the same and only the number of node fetches changes.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -102,27 +105,38 @@ struct RefTree {
     // std::stable_sort; large ones an LSD radix sort on the order-preserving integer image of the float key, which
     // is stable too and therefore yields the same permutation (-0.0 is folded onto +0.0 first, because the
     // comparison treats them as equal; midpoints are never NaN).
+    // scratch for the radix sort, indexed like the id array: concurrent subtree builds work on disjoint ranges
+    const uint32_t *ids_base = nullptr;
+    mutable std::vector<uint64_t> scratch_a, scratch_b;
     void sortAxis(int axis, uint32_t *ids, size_t n) const {
         const float *key = smid[axis].data();
         if (n < 4096) {
             std::stable_sort(ids, ids + n, [key](uint32_t a, uint32_t b) { return key[a] < key[b]; });
             return;
         }
-        std::vector<uint64_t> a(n), b(n); // (sortable key << 32) | id
+        uint64_t *a = scratch_a.data() + (ids - ids_base), *b = scratch_b.data() + (ids - ids_base); // (key << 32) | id
+        size_t count[4][257];
+        std::memset(count, 0, sizeof(count));
         for (size_t i = 0; i < n; i++) {
             uint32_t u;
             const float k = key[ids[i]] + 0.0f; // -0.0 + 0.0 = +0.0
             std::memcpy(&u, &k, 4);
             u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
             a[i] = ((uint64_t)u << 32) | ids[i];
+            count[0][(u & 0xff) + 1]++;
+            count[1][((u >> 8) & 0xff) + 1]++;
+            count[2][((u >> 16) & 0xff) + 1]++;
+            count[3][(u >> 24) + 1]++;
         }
         for (int pass = 0; pass < 4; pass++) {
-            size_t count[257] = {0};
+            size_t *c = count[pass];
+            bool trivial = false; // every key has the same digit: the pass would be the identity
+            for (int k = 1; k <= 256 && !trivial; k++) trivial = c[k] == n;
+            if (trivial) continue;
             const int shift = 32 + 8 * pass;
-            for (size_t i = 0; i < n; i++) count[((a[i] >> shift) & 0xff) + 1]++;
-            for (int k = 0; k < 256; k++) count[k + 1] += count[k];
-            for (size_t i = 0; i < n; i++) b[count[(a[i] >> shift) & 0xff]++] = a[i];
-            a.swap(b);
+            for (int k = 0; k < 256; k++) c[k + 1] += c[k];
+            for (size_t i = 0; i < n; i++) b[c[(a[i] >> shift) & 0xff]++] = a[i];
+            std::swap(a, b);
         }
         for (size_t i = 0; i < n; i++) ids[i] = (uint32_t)a[i];
     }
@@ -267,6 +281,7 @@ struct SahBuilder {
     std::vector<DevNode> *nodes;  // preallocated; build() hands slots out atomically, renumber() restores pre-order
     std::atomic<uint32_t> n_nodes{0};
     std::atomic<uint32_t> max_depth{0};
+    std::atomic<uint32_t> spawned{0};
     std::vector<float> cen[3];
 
     static float area(const Box &b) {
@@ -288,37 +303,49 @@ struct SahBuilder {
         constexpr int NB = 16;
         int best_axis = -1, best_bin = 0;
         float best_cost = std::numeric_limits<float>::infinity();
+        // one sweep over the primitives fills the bins of all three axes
+        Box bb[3][NB];
+        size_t cnt[3][NB];
+        float lo3[3], scale3[3];
+        bool use[3];
         for (int axis = 0; axis < 3; axis++) {
-            const float lo = cb.mn[axis], ext = cb.mx[axis] - cb.mn[axis];
-            if (!(ext > 0.0f)) continue;
-            Box bb[NB];
-            size_t cnt[NB] = {0};
-            for (auto &b : bb) b = boxEmpty();
-            const float scale = NB / ext;
-            for (size_t i = 0; i < n; i++) {
-                int b = (int)((cen[axis][ids[i]] - lo) * scale);
-                b = std::min(std::max(b, 0), NB - 1);
-                cnt[b]++;
-                bb[b] = boxUnion(bb[b], pbox[ids[i]]);
+            const float ext = cb.mx[axis] - cb.mn[axis];
+            use[axis] = ext > 0.0f;
+            lo3[axis] = cb.mn[axis];
+            scale3[axis] = use[axis] ? NB / ext : 0.0f;
+            for (int k = 0; k < NB; k++) { bb[axis][k] = boxEmpty(); cnt[axis][k] = 0; }
+        }
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t id = ids[i];
+            const Box &pb = pbox[id];
+            for (int axis = 0; axis < 3; axis++) {
+                if (!use[axis]) continue;
+                int k = (int)((cen[axis][id] - lo3[axis]) * scale3[axis]);
+                k = std::min(std::max(k, 0), NB - 1);
+                cnt[axis][k]++;
+                bb[axis][k] = boxUnion(bb[axis][k], pb);
             }
+        }
+        for (int axis = 0; axis < 3; axis++) {
+            if (!use[axis]) continue;
             float right_area[NB];
             size_t right_cnt[NB];
             Box acc = boxEmpty();
             size_t c = 0;
-            for (int b = NB - 1; b > 0; b--) {
-                acc = boxUnion(acc, bb[b]);
-                c += cnt[b];
-                right_area[b] = area(acc);
-                right_cnt[b] = c;
+            for (int k = NB - 1; k > 0; k--) {
+                acc = boxUnion(acc, bb[axis][k]);
+                c += cnt[axis][k];
+                right_area[k] = area(acc);
+                right_cnt[k] = c;
             }
             acc = boxEmpty();
             c = 0;
-            for (int b = 0; b < NB - 1; b++) {
-                acc = boxUnion(acc, bb[b]);
-                c += cnt[b];
-                if (c == 0 || right_cnt[b + 1] == 0) continue;
-                const float cost = area(acc) * (float)c + right_area[b + 1] * (float)right_cnt[b + 1];
-                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            for (int k = 0; k < NB - 1; k++) {
+                acc = boxUnion(acc, bb[axis][k]);
+                c += cnt[axis][k];
+                if (c == 0 || right_cnt[k + 1] == 0) continue;
+                const float cost = area(acc) * (float)c + right_area[k + 1] * (float)right_cnt[k + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = k; }
             }
         }
         size_t mid;
@@ -337,7 +364,10 @@ struct SahBuilder {
         }
         const uint32_t my = n_nodes.fetch_add(1);
         Emitted l, r;
-        if (depth <= RefTree::kParallelDepth && n >= RefTree::kParallelMin) {
+        // SAH splits are uneven (a ground sphere, a small mesh next to a big one), so the fan-out over host threads goes
+        // by subtree size, not by depth; `spawned` bounds the number of threads ever created per build
+        const size_t small = std::min(mid, n - mid);
+        if (small >= RefTree::kParallelMin && spawned.fetch_add(1) < 64) {
             std::thread left([&] { l = build(ids, mid, depth + 1); });
             r = build(ids + mid, n - mid, depth + 1);
             left.join();
@@ -371,10 +401,25 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
     *out = FlatBvh{};
     const size_t n = scene.surfaces.size();
     if (n == 0) return;
+    const bool timing = std::getenv("ZRT_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[zrt build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     RefTree rt(scene);
+    lap("surface boxes");
     std::vector<uint32_t> ids(n);
     for (size_t i = 0; i < n; i++) ids[i] = (uint32_t)i;
+    rt.ids_base = ids.data();
+    rt.scratch_a.resize(n);
+    rt.scratch_b.resize(n);
     const int32_t root = rt.divide(ids.data(), n, 1); // bvh.zig:171-185
+    std::vector<uint64_t>().swap(rt.scratch_a);
+    std::vector<uint64_t>().swap(rt.scratch_b);
+    lap("reference tree");
     out->ref_nodes = rt.n_nodes.load();
     out->ref_max_depth = rt.max_depth.load();
 
@@ -389,6 +434,7 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
         out->leaves += v;
         out->pruned += !v;
     }
+    lap("slots + flatten");
     if (sah && out->leaves > 1) {
         std::vector<Box> pbox;
         std::vector<uint32_t> pref;
@@ -407,11 +453,14 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
         }
         std::vector<uint32_t> pid(pbox.size());
         for (size_t i = 0; i < pid.size(); i++) pid[i] = (uint32_t)i;
+        lap("sah setup");
         const uint32_t root_ref = sb.build(pid.data(), pid.size(), 1).ref;
+        lap("sah build");
         out->nodes.clear();
         out->nodes.reserve(sb.n_nodes.load());
         out->root = sb.renumber(root_ref, scratch, &out->nodes);
         out->max_depth = sb.max_depth.load();
+        lap("sah renumber");
     }
 }
 
