@@ -158,3 +158,60 @@ def test_flattener_order_and_pruning_match_oracle_tree(name, fn):
     assert info.nodes == info.leaves - 1 and sah.nodes == info.nodes and sah.max_depth <= info.max_depth
     if name == "man":
         assert info.pruned_surfaces > 0  # Man.obj has axis-aligned flat triangles
+
+
+def _tie_heavy_scene(seed, n_tris, n_spheres):
+    """Surfaces whose box midpoints sit on a coarse lattice: every axis has long runs of exactly equal sort keys
+    (duplicates, -0.0 next to +0.0, axis-aligned flat triangles), the case in which the order a stable sort leaves
+    depends on the whole history of earlier sorts."""
+    from zraytrace_b200.scene import SceneBuilder
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder()
+    m = b.lambertian(b.color_texture(0.5, 0.5, 0.5))
+    cells = rng.integers(-3, 4, size=(n_tris, 3)).astype(np.float32)
+    half = rng.choice(np.array([0.5, 1.0], np.float32), size=(n_tris, 3))
+    flat = rng.random(n_tris) < 0.2
+    tris = np.zeros((n_tris, 3, 3), np.float32)
+    for i in range(n_tris):
+        lo, hi = cells[i] - half[i], cells[i] + half[i]
+        z_top = lo[2] if flat[i] else hi[2]  # flat: all three vertices share z, a zero-thickness box (Q4)
+        if flat[i] and z_top == 0.0 and rng.random() < 0.5:
+            lo[2] = z_top = np.float32(-0.0)  # midpoint -0.0: sorts as equal to +0.0
+        tris[i] = ((lo[0], lo[1], lo[2]), (hi[0], lo[1], z_top), (lo[0], hi[1], z_top))
+    b.triangles(tris, m)
+    for _ in range(n_spheres):
+        c = rng.integers(-3, 4, size=3).astype(np.float32)
+        b.sphere(tuple(float(x) for x in c), float(rng.choice([0.25, 0.5, -0.5])), m)
+    return b.build()
+
+
+@pytest.mark.parametrize("seed,n_tris,n_spheres", [(1, 2500, 40), (2, 6000, 0), (3, 2100, 300)])
+def test_presorted_tree_build_matches_oracle_on_tie_heavy_scenes(seed, n_tris, n_spheres):
+    """Above 2048 surfaces the reference tree is rebuilt from five presorted index lists instead of by sorting
+    inside the recursion (zrt_flatten.cpp); the oracle's pointer tree sorts literally like bvh.zig:71-120."""
+    sc = _tie_heavy_scene(seed, n_tris, n_spheres)
+    o_order, o_vis, st = zro_py.bvh_order(sc)
+    with Z.Scene(sc, device=-1) as hs:
+        z_order, z_vis = hs.bvh_order()
+        info = hs.bvh_info(A.ZRT_FLAG_BVH_REFERENCE)
+    assert np.array_equal(o_order, z_order) and np.array_equal(o_vis, z_vis)
+    assert info.reference_nodes == st.bvh_nodes and info.reference_max_depth == st.bvh_max_depth
+    assert (~o_vis).sum() > 0
+
+
+def test_presorted_tree_build_matches_literal_build_on_config4(monkeypatch):
+    """317 952 + 3 933 triangles: the presorted build and the literal sort-in-the-recursion build of the same
+    library (ZRT_BVH_BUILD=literal) give the same DFS order, pruning, node count and depth."""
+    hsrc = host.HostScene(host.SCENE_GOAT, variant=host.VARIANT_GOAT_SUBSTITUTE, aspect_ratio=16 / 9)
+    got = []
+    for how in ("literal", "presorted"):
+        monkeypatch.setenv("ZRT_BVH_BUILD", how)
+        with Z.Scene(hsrc.desc, device=-1) as s:
+            order, vis = s.bvh_order()
+            info = s.bvh_info(A.ZRT_FLAG_BVH_REFERENCE)
+            sah = s.bvh_info()
+            got.append((order.copy(), vis.copy(), info.reference_nodes, info.reference_max_depth, info.nodes,
+                        info.max_depth, sah.nodes, sah.max_depth))
+    hsrc.close()
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    assert got[0][2:] == got[1][2:]

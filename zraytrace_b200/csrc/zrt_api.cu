@@ -268,6 +268,7 @@ int buildListRep(zrt_scene *sc, DevRep &r) {
 int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
     const HostScene &hs = sc->host;
     build_flat_bvh(hs, sah, &r.info);
+    BuildLap lap;
     if (r.info.max_depth + 2 >= (uint32_t)TRAVERSAL_STACK)
         return fail(ZRT_ERR_INVALID, "BVH deeper than the traversal stack; drop ZRT_FLAG_BVH_REFERENCE");
     const uint32_t slots = (uint32_t)r.info.slot_surface.size();
@@ -279,11 +280,14 @@ int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
     for (uint32_t s = 0; s < slots; s++) slot_of[r.info.slot_surface[s]] = s;
     for (uint32_t i = 0; i < hs.surfaces.size(); i++)
         if (hs.surfaces[i].kind == ZRT_SURFACE_SPHERE) r.h_spheres.push_back(makeSphere(hs, i, slot_of[i]));
-    for (uint32_t s = 0; s < slots; s++) {
-        const uint32_t surf = r.info.slot_surface[s];
-        if (hs.surfaces[surf].kind == ZRT_SURFACE_TRIANGLE) makeTriangle(hs, surf, &A[s], &E1[s], &E2[s], &meta[s]);
-        else { A[s] = E1[s] = E2[s] = float4{0, 0, 0, 0}; meta[s] = TriMeta{0, surf}; }
-    }
+    parallelFor(slots, 16384, [&](size_t begin, size_t end) {
+        for (size_t s = begin; s < end; s++) {
+            const uint32_t surf = r.info.slot_surface[s];
+            if (hs.surfaces[surf].kind == ZRT_SURFACE_TRIANGLE) makeTriangle(hs, surf, &A[s], &E1[s], &E2[s], &meta[s]);
+            else { A[s] = E1[s] = E2[s] = float4{0, 0, 0, 0}; meta[s] = TriMeta{0, surf}; }
+        }
+    });
+    lap("pack primitives");
     r.n_spheres = (uint32_t)r.h_spheres.size();
     r.n_list = 0;
     r.root = r.info.root;
@@ -292,6 +296,7 @@ int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
     CUDA_TRY(r.triA.upload(A)); CUDA_TRY(r.triE1.upload(E1)); CUDA_TRY(r.triE2.upload(E2));
     CUDA_TRY(r.triMeta.upload(meta));
     CUDA_TRY(r.nodes.upload(r.info.nodes));
+    lap("upload");
     r.ready = true;
     return ZRT_OK;
 }

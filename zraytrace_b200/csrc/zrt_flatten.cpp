@@ -19,29 +19,39 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <thread>
+#if defined(__SSE__)
+#include <xmmintrin.h>
+#endif
 
 #include "zrt_internal.h"
 
 namespace zrt {
 namespace {
 
-struct Box {
-    float mn[3], mx[3];
+struct alignas(16) Box {
+    float mn[4], mx[4]; // lane 3 is padding (one SSE register per corner)
 };
 inline float zmin(float x, float y) { return (x < y) ? x : y; } // Zig std.math.min
 inline float zmax(float x, float y) { return (x > y) ? x : y; }
 inline Box boxUnion(const Box &a, const Box &b) { // aabb.zig:68-71
     Box r;
-    for (int i = 0; i < 3; i++) {
+#if defined(__SSE__)
+    // MINPS / MAXPS are exactly the two ternaries above, operand order included (second operand on equality)
+    _mm_store_ps(r.mn, _mm_min_ps(_mm_load_ps(a.mn), _mm_load_ps(b.mn)));
+    _mm_store_ps(r.mx, _mm_max_ps(_mm_load_ps(a.mx), _mm_load_ps(b.mx)));
+#else
+    for (int i = 0; i < 4; i++) {
         r.mn[i] = zmin(a.mn[i], b.mn[i]);
         r.mx[i] = zmax(a.mx[i], b.mx[i]);
     }
+#endif
     return r;
 }
 inline Box boxEmpty() {
     const float inf = std::numeric_limits<float>::infinity();
-    return Box{{inf, inf, inf}, {-inf, -inf, -inf}};
+    return Box{{inf, inf, inf, inf}, {-inf, -inf, -inf, -inf}};
 }
 inline bool boxFlat(const Box &b) { return b.mn[0] == b.mx[0] || b.mn[1] == b.mx[1] || b.mn[2] == b.mx[2]; }
 inline float boxScore(const Box &b) { // aabb.zig:99-105: 2*(dx^2+dy^2+dz^2), not an area
@@ -72,8 +82,8 @@ struct RefTree {
         nodes.resize(2 * n + 2);
         sbox.resize(n);
         for (auto &m : smid) m.resize(n);
-        for (size_t i = 0; i < n; i++) {
-            Box b;
+        parallelFor(n, 16384, [this](size_t begin, size_t end) { for (size_t i = begin; i < end; i++) {
+            Box b{};
             if (sc.surfaces[i].kind == ZRT_SURFACE_SPHERE) { // sphere.zig:24-29
                 const zrt_sphere &s = sc.spheres[sc.surfaces[i].index];
                 const float c[3] = {s.center.x, s.center.y, s.center.z};
@@ -93,7 +103,7 @@ struct RefTree {
                 }
             }
             sbox[i] = b;
-        }
+        } });
     }
 
     Box rangeBox(const uint32_t *ids, size_t n) const { // bvh.zig:62-69 surfaces_to_aabb (min/max are exact)
@@ -104,17 +114,13 @@ struct RefTree {
     // bvh.zig:71-72: std.sort.sort is a stable comparison sort on `a.midpoint < b.midpoint`.  Small ranges use
     // std::stable_sort; large ones an LSD radix sort on the order-preserving integer image of the float key, which
     // is stable too and therefore yields the same permutation (-0.0 is folded onto +0.0 first, because the
-    // comparison treats them as equal; midpoints are never NaN).
-    // scratch for the radix sort, indexed like the id array: concurrent subtree builds work on disjoint ranges
-    const uint32_t *ids_base = nullptr;
-    mutable std::vector<uint64_t> scratch_a, scratch_b;
-    void sortAxis(int axis, uint32_t *ids, size_t n) const {
+    // comparison treats them as equal; midpoints are never NaN).  a, b: scratch of n (key << 32 | id) words.
+    void sortAxis(int axis, uint32_t *ids, size_t n, uint64_t *a, uint64_t *b) const {
         const float *key = smid[axis].data();
         if (n < 4096) {
-            std::stable_sort(ids, ids + n, [key](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+            std::stable_sort(ids, ids + n, [key](uint32_t x, uint32_t y) { return key[x] < key[y]; });
             return;
         }
-        uint64_t *a = scratch_a.data() + (ids - ids_base), *b = scratch_b.data() + (ids - ids_base); // (key << 32) | id
         size_t count[4][257];
         std::memset(count, 0, sizeof(count));
         for (size_t i = 0; i < n; i++) {
@@ -140,45 +146,67 @@ struct RefTree {
         }
         for (size_t i = 0; i < n; i++) ids[i] = (uint32_t)a[i];
     }
-    // bvh.zig:85-120.  The reference re-sorts before each of the three candidate splits of an axis;
-    // the 2nd and 3rd sort of an already sorted range by the same key with a stable sort change
-    // nothing, so one sort per axis reproduces the same permutation sequence.
-    size_t optimalAxisDivide(uint32_t *ids, size_t n) const {
+    // scratch for the literal build, indexed like the id array: concurrent subtree builds work on disjoint ranges
+    const uint32_t *ids_base = nullptr;
+    mutable std::vector<uint64_t> scratch_a, scratch_b;
+    void sortAxis(int axis, uint32_t *ids, size_t n) const {
+        if (n < 4096) sortAxis(axis, ids, n, nullptr, nullptr);
+        else sortAxis(axis, ids, n, scratch_a.data() + (ids - ids_base), scratch_b.data() + (ids - ids_base));
+    }
+    // bvh.zig:85-120: candidate splits at n/4, n/2, n/4 + n/2 (n/2 alone below four surfaces) on each axis; the
+    // first strictly smaller (left score + right score) / total score wins, axes in x, y, z order.
+    struct SplitSearch {
+        size_t splits[3];
+        int n_splits;
+        float total = 0.0f;
         int best_axis = 0;
         float best_ratio = std::numeric_limits<float>::infinity();
-        size_t best_split = n / 2;
-        const float total = boxScore(rangeBox(ids, n));
-        size_t splits[3] = {n / 2, 0, 0};
-        int n_splits = 1;
-        if (n >= 4) {
-            splits[0] = n / 4; splits[1] = n / 2; splits[2] = n / 4 + n / 2;
-            n_splits = 3;
+        size_t best_split;
+        explicit SplitSearch(size_t n) : splits{n / 2, 0, 0}, n_splits(1), best_split(n / 2) {
+            if (n >= 4) {
+                splits[0] = n / 4; splits[1] = n / 2; splits[2] = n / 4 + n / 2;
+                n_splits = 3;
+            }
         }
+    };
+    // boxes of the segments between consecutive split points of a range sorted on one axis; the halves of every
+    // candidate split (and the box of the whole range) are exact unions of them
+    void segmentBoxes(const SplitSearch &ss, const uint32_t *ids, size_t n, Box seg[4]) const {
+        size_t lo = 0;
+        for (int k = 0; k <= ss.n_splits; k++) {
+            const size_t hi = (k < ss.n_splits) ? ss.splits[k] : n;
+            seg[k] = rangeBox(ids + lo, hi - lo);
+            lo = hi;
+        }
+    }
+    static void scoreAxis(SplitSearch &ss, int axis, const Box seg[4]) {
+        for (int k = 0; k < ss.n_splits; k++) {
+            Box left = boxEmpty(), right = boxEmpty();
+            for (int j = 0; j <= k; j++) left = boxUnion(left, seg[j]);
+            for (int j = k + 1; j <= ss.n_splits; j++) right = boxUnion(right, seg[j]);
+            const float area = boxScore(right) + boxScore(left);
+            const float ratio = area / ss.total;
+            if (ratio < ss.best_ratio) {
+                ss.best_ratio = ratio;
+                ss.best_axis = axis;
+                ss.best_split = ss.splits[k];
+            }
+        }
+    }
+    // The literal sequence.  The reference re-sorts before each of the three candidate splits of an axis; the 2nd
+    // and 3rd sort of an already sorted range by the same key with a stable sort change nothing, so one sort per
+    // axis reproduces the same permutation sequence.
+    size_t optimalAxisDivide(uint32_t *ids, size_t n) const {
+        SplitSearch ss(n);
+        ss.total = boxScore(rangeBox(ids, n));
         for (int axis = 0; axis < 3; axis++) {
             sortAxis(axis, ids, n);
-            // boxes of the segments between consecutive split points; halves are exact unions of them
             Box seg[4];
-            size_t lo = 0;
-            for (int k = 0; k <= n_splits; k++) {
-                const size_t hi = (k < n_splits) ? splits[k] : n;
-                seg[k] = rangeBox(ids + lo, hi - lo);
-                lo = hi;
-            }
-            for (int k = 0; k < n_splits; k++) {
-                Box left = boxEmpty(), right = boxEmpty();
-                for (int j = 0; j <= k; j++) left = boxUnion(left, seg[j]);
-                for (int j = k + 1; j <= n_splits; j++) right = boxUnion(right, seg[j]);
-                const float area = boxScore(right) + boxScore(left);
-                const float ratio = area / total;
-                if (ratio < best_ratio) {
-                    best_ratio = ratio;
-                    best_axis = axis;
-                    best_split = splits[k];
-                }
-            }
+            segmentBoxes(ss, ids, n, seg);
+            scoreAxis(ss, axis, seg);
         }
-        sortAxis(best_axis, ids, n); // "redo the best split"
-        return best_split;
+        sortAxis(ss.best_axis, ids, n); // "redo the best split"
+        return ss.best_split;
     }
     const Box &childBox(int32_t c) const { return c >= 0 ? nodes[c].box : sbox[~c]; }
     int32_t create(int32_t left, int32_t right) { // bvh.zig:162-169
@@ -202,6 +230,169 @@ struct RefTree {
             r = divide(ids + split, n - split, depth + 1);
         }
         return create(l, r);
+    }
+
+    // ---- the same tree without sorting inside the recursion ------------------------------------------------------
+    // Every sort above is stable, so the order of a range after a sort is a fixed lexicographic order on the three
+    // midpoint keys, ending in the input index, that does not depend on the range.  With F(p) the order the parent
+    // left its range in, a node sees
+    //      after the x sort   (x, F(p))          after the y sort   (y, x, F(p)) = (y, x, z, idx)
+    //      after the z sort   (z, y, x, idx)     after the redo     (b, z, y, x, idx) = F(node), b the winning axis
+    // and (x, F(p)) is (x, y, z, idx) if the parent split on y, (x, z, y, idx) otherwise.  That is five global orders;
+    // they are sorted once (ten stable one-key sorts, the ones the reference does at its root among them) and every
+    // split then partitions the five index lists stably instead of re-sorting: O(n) per node.  The root is the one
+    // node whose incoming order is the input order itself: its x and y sorts give (x, idx) and (y, x, idx).
+    // Ranges below kLiteralBelow run the literal code on a copy of the range in the parent's order.
+    enum Order { O_XZY = 0, O_XYZ = 1, O_YXZ = 2, O_ZYX = 3, O_YZX = 4, N_ORDERS = 5 };
+    static constexpr size_t kPresortMin = 2048;
+    static constexpr size_t kLiteralBelow = 3;
+    std::vector<uint32_t> ord[N_ORDERS];
+    std::vector<uint32_t> part_tmp; // scratch of the partitions, indexed like the lists
+    std::vector<uint8_t> side;      // per surface: which half of the current split it went to
+    std::atomic<uint32_t> spawned{0};
+
+    // One of the global orders (k0, k1, k2, idx) from the list sorted on (k0, idx): only runs of equal k0 are out of
+    // place, and within a run the order is (k1, k2, idx).  Ties between midpoints are rare in a mesh, so this is a
+    // scan; a run as long as the list (a flat sheet of triangles) costs one comparison sort.
+    void refineRuns(const std::vector<uint32_t> &base, int k0, int k1, int k2, std::vector<uint32_t> *out) const {
+        *out = base;
+        const float *a = smid[k0].data(), *b = smid[k1].data(), *c = k2 >= 0 ? smid[k2].data() : nullptr;
+        uint32_t *ids = out->data();
+        const size_t n = out->size();
+        for (size_t i = 0; i < n;) {
+            size_t j = i + 1;
+            while (j < n && a[ids[j]] == a[ids[i]]) j++; // == is the comparator's notion of a tie (-0.0 == +0.0)
+            if (j - i > 1)
+                std::sort(ids + i, ids + j, [b, c](uint32_t p, uint32_t q) {
+                    if (b[p] != b[q]) return b[p] < b[q];
+                    if (c && c[p] != c[q]) return c[p] < c[q];
+                    return p < q;
+                });
+            i = j;
+        }
+    }
+    static constexpr size_t kWideNode = 65536; // above this the passes over one node run on separate threads too
+    void partitionList(int k, size_t lo, size_t n, uint32_t *tmp) {
+        uint32_t *list = ord[k].data() + lo;
+        size_t a = 0, b = 0;
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t id = list[i];
+            if (side[id]) tmp[b++] = id;
+            else list[a++] = id;
+        }
+        std::memcpy(list + a, tmp, b * sizeof(uint32_t));
+    }
+    void partitionLists(size_t lo, size_t n, int final_order, size_t at) {
+        const uint32_t *f = ord[final_order].data() + lo;
+        for (size_t i = 0; i < at; i++) side[f[i]] = 0;
+        for (size_t i = at; i < n; i++) side[f[i]] = 1;
+        if (n >= kWideNode) { // four lists, four threads (the final order's own list doubles as the fourth scratch)
+            std::thread th[N_ORDERS];
+            std::vector<uint32_t> extra[N_ORDERS];
+            int used = 0;
+            for (int k = 0; k < N_ORDERS; k++) {
+                if (k == final_order) continue;
+                uint32_t *tmp = part_tmp.data() + lo;
+                if (used++) { extra[k].resize(n); tmp = extra[k].data(); }
+                th[k] = std::thread([this, k, lo, n, tmp] { partitionList(k, lo, n, tmp); });
+            }
+            for (int k = 0; k < N_ORDERS; k++) if (k != final_order) th[k].join();
+            return;
+        }
+        for (int k = 0; k < N_ORDERS; k++)
+            if (k != final_order) partitionList(k, lo, n, part_tmp.data() + lo);
+    }
+    int32_t splitPresorted(size_t lo, size_t n, const uint32_t *const lists[3], uint32_t depth) {
+        SplitSearch ss(n);
+        Box seg[3][4];
+        if (n >= kWideNode) {
+            std::thread ty([&] { segmentBoxes(ss, lists[1], n, seg[1]); });
+            std::thread tz([&] { segmentBoxes(ss, lists[2], n, seg[2]); });
+            segmentBoxes(ss, lists[0], n, seg[0]);
+            ty.join();
+            tz.join();
+        } else {
+            for (int axis = 0; axis < 3; axis++) segmentBoxes(ss, lists[axis], n, seg[axis]);
+        }
+        Box whole = boxEmpty();
+        for (int k = 0; k <= ss.n_splits; k++) whole = boxUnion(whole, seg[0][k]);
+        ss.total = boxScore(whole);
+        for (int axis = 0; axis < 3; axis++) scoreAxis(ss, axis, seg[axis]);
+        const int final_order = ss.best_axis == 0 ? O_XZY : (ss.best_axis == 1 ? O_YZX : O_ZYX);
+        const int child_x = ss.best_axis == 1 ? O_XYZ : O_XZY;
+        const size_t at = ss.best_split;
+        partitionLists(lo, n, final_order, at);
+        int32_t l, r;
+        if (std::min(at, n - at) >= kParallelMin && spawned.fetch_add(1) < 64) {
+            std::thread left([&] { l = dividePresorted(lo, at, final_order, child_x, depth + 1); });
+            r = dividePresorted(lo + at, n - at, final_order, child_x, depth + 1);
+            left.join();
+        } else {
+            l = dividePresorted(lo, at, final_order, child_x, depth + 1);
+            r = dividePresorted(lo + at, n - at, final_order, child_x, depth + 1);
+        }
+        return create(l, r);
+    }
+    int32_t dividePresorted(size_t lo, size_t n, int parent_final, int x_order, uint32_t depth) {
+        if (n < kLiteralBelow) {
+            uint32_t ids[kLiteralBelow];
+            std::memcpy(ids, ord[parent_final].data() + lo, n * sizeof(uint32_t));
+            return divide(ids, n, depth);
+        }
+        uint32_t seen = max_depth.load();
+        while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
+        const uint32_t *const lists[3] = {ord[x_order].data() + lo, ord[O_YXZ].data() + lo, ord[O_ZYX].data() + lo};
+        return splitPresorted(lo, n, lists, depth);
+    }
+    int32_t buildPresorted() {
+        const size_t n = sc.surfaces.size();
+        const auto t_start = std::chrono::steady_clock::now();
+        std::vector<uint32_t> idx(n), root_x, root_y;
+        for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
+        {
+            std::vector<uint32_t> base[3]; // (x, idx), (y, idx), (z, idx): the one-key sorts of the input order
+            auto sortBase = [&](int axis) {
+                std::vector<uint64_t> sa(n), sb(n);
+                base[axis] = idx;
+                sortAxis(axis, base[axis].data(), n, sa.data(), sb.data());
+            };
+            std::thread ty([&] {
+                sortBase(1);
+                std::thread t1([&] { refineRuns(base[1], 1, 2, 0, &ord[O_YZX]); });
+                std::thread t2([&] { refineRuns(base[1], 1, 0, -1, &root_y); }); // (y, x, idx): the root's y sort
+                refineRuns(base[1], 1, 0, 2, &ord[O_YXZ]);
+                t1.join();
+                t2.join();
+            });
+            std::thread tz([&] { sortBase(2); refineRuns(base[2], 2, 1, 0, &ord[O_ZYX]); });
+            sortBase(0);
+            std::thread tx([&] { refineRuns(base[0], 0, 1, 2, &ord[O_XYZ]); });
+            refineRuns(base[0], 0, 2, 1, &ord[O_XZY]);
+            tx.join();
+            ty.join();
+            tz.join();
+            root_x.swap(base[0]); // (x, idx): the root's x sort
+        }
+        part_tmp.resize(n);
+        side.resize(n);
+        max_depth.store(1);
+        if (std::getenv("ZRT_TIMING")) {
+            const auto t1 = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[zrt build]   of which presort     %8.1f ms\n", std::chrono::duration<double, std::milli>(t1 - t_start).count());
+        }
+        const uint32_t *const lists[3] = {root_x.data(), root_y.data(), ord[O_ZYX].data()};
+        return splitPresorted(0, n, lists, 1);
+    }
+    int32_t build(std::vector<uint32_t> *ids, bool literal) {
+        const size_t n = ids->size();
+        if (!literal && n >= kPresortMin) return buildPresorted();
+        ids_base = ids->data();
+        scratch_a.resize(n);
+        scratch_b.resize(n);
+        const int32_t root = divide(ids->data(), n, 1); // bvh.zig:171-185
+        std::vector<uint64_t>().swap(scratch_a);
+        std::vector<uint64_t>().swap(scratch_b);
+        return root;
     }
 };
 
@@ -250,6 +441,18 @@ struct Flattener {
         alive[c] = ok ? 1 : 0;
         return ok;
     }
+    // precondition: survives(c).  emit() without the nodes: only marks the surfaces the reference can reach
+    // (all the SAH rebuild needs from the reference topology).
+    void markVisible(int32_t c) {
+        for (;;) {
+            if (c < 0) { leafRef((uint32_t)~c); return; }
+            const RefNode &n = rt.nodes[c];
+            if (n.left == n.right && n.left < 0) { leafRef((uint32_t)~n.left); return; }
+            const bool sl = survives(n.left), sr = survives(n.right);
+            if (sl && sr) markVisible(n.left);
+            c = sr ? n.right : n.left;
+        }
+    }
     // precondition: survives(c)
     Emitted emit(int32_t c, uint32_t depth) {
         if (c < 0) return Emitted{leafRef((uint32_t)~c), rt.sbox[~c]};
@@ -278,8 +481,10 @@ struct Flattener {
 struct SahBuilder {
     const std::vector<Box> &pbox; // per primitive
     const std::vector<uint32_t> &pref; // per primitive leaf ref
-    std::vector<DevNode> *nodes;  // preallocated; build() hands slots out atomically, renumber() restores pre-order
-    std::atomic<uint32_t> n_nodes{0};
+    // preallocated, one node per split.  A subtree over m primitives has exactly m - 1 nodes, so DFS pre-order
+    // numbers (parent before its subtrees, left subtree contiguous: memory locality of the traversal, and a node order
+    // that does not depend on thread timing) are known on the way down: left child = my + 1, right = my + |left|.
+    std::vector<DevNode> *nodes;
     std::atomic<uint32_t> max_depth{0};
     std::atomic<uint32_t> spawned{0};
     std::vector<float> cen[3];
@@ -288,24 +493,45 @@ struct SahBuilder {
         const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
         return 2.0f * (dx * dy + dy * dz + dz * dx);
     }
-    Emitted build(uint32_t *ids, size_t n, uint32_t depth) {
+    Emitted build(uint32_t *ids, size_t n, uint32_t depth, uint32_t my) {
         if (n == 1) return Emitted{pref[ids[0]], pbox[ids[0]]};
         uint32_t seen = max_depth.load();
         while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
-        Box bounds = boxEmpty(), cb = boxEmpty();
-        for (size_t i = 0; i < n; i++) {
-            bounds = boxUnion(bounds, pbox[ids[i]]);
-            for (int k = 0; k < 3; k++) {
-                cb.mn[k] = std::min(cb.mn[k], cen[k][ids[i]]);
-                cb.mx[k] = std::max(cb.mx[k], cen[k][ids[i]]);
-            }
+        // the passes over a wide node are split over host threads: min / max and counts merge exactly, so the tree does
+        // not depend on how many threads there are
+        constexpr size_t kWide = 65536, kChunk = 16384;
+        Box cb = boxEmpty();
+        {
+            std::mutex m;
+            parallelFor(n >= kWide ? n : 1, kChunk, [&](size_t begin, size_t end) {
+                if (n < kWide) end = n;
+                Box c = boxEmpty();
+                for (size_t i = begin; i < end; i++)
+                    for (int k = 0; k < 3; k++) {
+                        c.mn[k] = std::min(c.mn[k], cen[k][ids[i]]);
+                        c.mx[k] = std::max(c.mx[k], cen[k][ids[i]]);
+                    }
+                std::lock_guard<std::mutex> g(m);
+                for (int k = 0; k < 3; k++) {
+                    cb.mn[k] = std::min(cb.mn[k], c.mn[k]);
+                    cb.mx[k] = std::max(cb.mx[k], c.mx[k]);
+                }
+            });
         }
         constexpr int NB = 16;
         int best_axis = -1, best_bin = 0;
         float best_cost = std::numeric_limits<float>::infinity();
         // one sweep over the primitives fills the bins of all three axes
-        Box bb[3][NB];
-        size_t cnt[3][NB];
+        struct Bins {
+            Box bb[3][NB];
+            size_t cnt[3][NB];
+        };
+        Bins bins;
+        auto clearBins = [](Bins &b) {
+            for (int axis = 0; axis < 3; axis++)
+                for (int k = 0; k < NB; k++) { b.bb[axis][k] = boxEmpty(); b.cnt[axis][k] = 0; }
+        };
+        clearBins(bins);
         float lo3[3], scale3[3];
         bool use[3];
         for (int axis = 0; axis < 3; axis++) {
@@ -313,19 +539,38 @@ struct SahBuilder {
             use[axis] = ext > 0.0f;
             lo3[axis] = cb.mn[axis];
             scale3[axis] = use[axis] ? NB / ext : 0.0f;
-            for (int k = 0; k < NB; k++) { bb[axis][k] = boxEmpty(); cnt[axis][k] = 0; }
         }
-        for (size_t i = 0; i < n; i++) {
-            const uint32_t id = ids[i];
-            const Box &pb = pbox[id];
-            for (int axis = 0; axis < 3; axis++) {
-                if (!use[axis]) continue;
-                int k = (int)((cen[axis][id] - lo3[axis]) * scale3[axis]);
-                k = std::min(std::max(k, 0), NB - 1);
-                cnt[axis][k]++;
-                bb[axis][k] = boxUnion(bb[axis][k], pb);
+        auto fill = [&](Bins &b, size_t begin, size_t end) {
+            for (size_t i = begin; i < end; i++) {
+                const uint32_t id = ids[i];
+                const Box &pb = pbox[id];
+                for (int axis = 0; axis < 3; axis++) {
+                    if (!use[axis]) continue;
+                    int k = (int)((cen[axis][id] - lo3[axis]) * scale3[axis]);
+                    k = std::min(std::max(k, 0), NB - 1);
+                    b.cnt[axis][k]++;
+                    b.bb[axis][k] = boxUnion(b.bb[axis][k], pb);
+                }
             }
+        };
+        if (n >= kWide) {
+            std::mutex m;
+            parallelFor(n, kChunk, [&](size_t begin, size_t end) {
+                Bins local;
+                clearBins(local);
+                fill(local, begin, end);
+                std::lock_guard<std::mutex> g(m);
+                for (int axis = 0; axis < 3; axis++)
+                    for (int k = 0; k < NB; k++) {
+                        bins.bb[axis][k] = boxUnion(bins.bb[axis][k], local.bb[axis][k]);
+                        bins.cnt[axis][k] += local.cnt[axis][k];
+                    }
+            });
+        } else {
+            fill(bins, 0, n);
         }
+        auto &bb = bins.bb;
+        auto &cnt = bins.cnt;
         for (int axis = 0; axis < 3; axis++) {
             if (!use[axis]) continue;
             float right_area[NB];
@@ -362,36 +607,23 @@ struct SahBuilder {
             mid = (size_t)(m - ids);
             if (mid == 0 || mid == n) mid = n / 2;
         }
-        const uint32_t my = n_nodes.fetch_add(1);
         Emitted l, r;
         // SAH splits are uneven (a ground sphere, a small mesh next to a big one), so the fan-out over host threads goes
         // by subtree size, not by depth; `spawned` bounds the number of threads ever created per build
         const size_t small = std::min(mid, n - mid);
         if (small >= RefTree::kParallelMin && spawned.fetch_add(1) < 64) {
-            std::thread left([&] { l = build(ids, mid, depth + 1); });
-            r = build(ids + mid, n - mid, depth + 1);
+            std::thread left([&] { l = build(ids, mid, depth + 1, my + 1); });
+            r = build(ids + mid, n - mid, depth + 1, my + (uint32_t)mid);
             left.join();
         } else {
-            l = build(ids, mid, depth + 1);
-            r = build(ids + mid, n - mid, depth + 1);
+            l = build(ids, mid, depth + 1, my + 1);
+            r = build(ids + mid, n - mid, depth + 1, my + (uint32_t)mid);
         }
         DevNode &d = (*nodes)[my];
         d.set_box(0, l.box.mn, l.box.mx);
         d.set_box(1, r.box.mn, r.box.mx);
         d.left = l.ref; d.right = r.ref; d.pad0 = d.pad1 = 0;
         return Emitted{my, boxUnion(l.box, r.box)};
-    }
-    // DFS pre-order renumbering (parent before its subtrees, left subtree contiguous): memory locality of the
-    // traversal, and a node order that does not depend on thread timing
-    uint32_t renumber(uint32_t ref, const std::vector<DevNode> &src, std::vector<DevNode> *dst) const {
-        if (ref & REF_LEAF) return ref;
-        const uint32_t my = (uint32_t)dst->size();
-        dst->push_back(src[ref]);
-        const uint32_t l = renumber(src[ref].left, src, dst);
-        const uint32_t r = renumber(src[ref].right, src, dst);
-        (*dst)[my].left = l;
-        (*dst)[my].right = r;
-        return my;
     }
 };
 
@@ -401,24 +633,15 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
     *out = FlatBvh{};
     const size_t n = scene.surfaces.size();
     if (n == 0) return;
-    const bool timing = std::getenv("ZRT_TIMING") != nullptr;
-    auto t0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char *what) {
-        if (!timing) return;
-        auto t1 = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[zrt build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    };
+    BuildLap lap_timer;
+    auto lap = [&](const char *what) { lap_timer(what); };
     RefTree rt(scene);
     lap("surface boxes");
     std::vector<uint32_t> ids(n);
     for (size_t i = 0; i < n; i++) ids[i] = (uint32_t)i;
-    rt.ids_base = ids.data();
-    rt.scratch_a.resize(n);
-    rt.scratch_b.resize(n);
-    const int32_t root = rt.divide(ids.data(), n, 1); // bvh.zig:171-185
-    std::vector<uint64_t>().swap(rt.scratch_a);
-    std::vector<uint64_t>().swap(rt.scratch_b);
+    // ZRT_BVH_BUILD=literal: the sort-in-the-recursion rebuild at every size (the presorted build's cross-check)
+    const char *how = std::getenv("ZRT_BVH_BUILD");
+    const int32_t root = rt.build(&ids, how && std::strcmp(how, "literal") == 0);
     lap("reference tree");
     out->ref_nodes = rt.n_nodes.load();
     out->ref_max_depth = rt.max_depth.load();
@@ -428,16 +651,33 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
     uint32_t nsph = 0;
     for (size_t i = 0; i < n; i++)
         if (scene.surfaces[i].kind == ZRT_SURFACE_SPHERE) fl.sphere_seq[i] = nsph++;
+    out->slot_surface.reserve(n);
+    out->slot_visible.reserve(n);
     fl.assignSlots(root);
-    out->root = fl.survives(root) ? fl.emit(root, 1).ref : REF_EMPTY;
-    for (uint8_t v : out->slot_visible) {
-        out->leaves += v;
-        out->pruned += !v;
+    lap("slots");
+    auto countLeaves = [&] {
+        out->leaves = out->pruned = 0;
+        for (uint8_t v : out->slot_visible) {
+            out->leaves += v;
+            out->pruned += !v;
+        }
+    };
+    const bool any = fl.survives(root);
+    if (sah && any) {
+        fl.markVisible(root);
+        countLeaves();
+    }
+    if (!sah || out->leaves <= 1) { // the reference topology itself (also when there is nothing to re-split)
+        out->nodes.reserve(n);
+        out->root = any ? fl.emit(root, 1).ref : REF_EMPTY;
+        countLeaves();
     }
     lap("slots + flatten");
     if (sah && out->leaves > 1) {
         std::vector<Box> pbox;
         std::vector<uint32_t> pref;
+        pbox.reserve(out->leaves);
+        pref.reserve(out->leaves);
         for (size_t s = 0; s < out->slot_surface.size(); s++) {
             if (!out->slot_visible[s]) continue;
             const uint32_t surf = out->slot_surface[s];
@@ -445,8 +685,9 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
             pref.push_back(scene.surfaces[surf].kind == ZRT_SURFACE_SPHERE ? (REF_LEAF | REF_SPHERE | fl.sphere_seq[surf])
                                                                            : (REF_LEAF | (uint32_t)s));
         }
-        std::vector<DevNode> scratch(pbox.size() + 1);
-        SahBuilder sb{pbox, pref, &scratch};
+        out->nodes.clear();
+        out->nodes.resize(pbox.size() - 1);
+        SahBuilder sb{pbox, pref, &out->nodes, {}, {}, {}};
         for (int k = 0; k < 3; k++) {
             sb.cen[k].resize(pbox.size());
             for (size_t i = 0; i < pbox.size(); i++) sb.cen[k][i] = 0.5f * (pbox[i].mn[k] + pbox[i].mx[k]);
@@ -454,13 +695,9 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
         std::vector<uint32_t> pid(pbox.size());
         for (size_t i = 0; i < pid.size(); i++) pid[i] = (uint32_t)i;
         lap("sah setup");
-        const uint32_t root_ref = sb.build(pid.data(), pid.size(), 1).ref;
-        lap("sah build");
-        out->nodes.clear();
-        out->nodes.reserve(sb.n_nodes.load());
-        out->root = sb.renumber(root_ref, scratch, &out->nodes);
+        out->root = sb.build(pid.data(), pid.size(), 1, 0).ref;
         out->max_depth = sb.max_depth.load();
-        lap("sah renumber");
+        lap("sah build");
     }
 }
 

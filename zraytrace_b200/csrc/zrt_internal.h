@@ -1,8 +1,13 @@
 // zrt_internal.h — flattened scene layout shared by the host flattener and the sm_100a kernels.
 // Everything here is resident in HBM (in practice L1/L2: a scene is at most a few MB).
 #pragma once
+#include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zrt.h"
@@ -139,6 +144,32 @@ struct KParams {
 };
 
 enum TraceMode { MODE_SPHERES = 0, MODE_LIST = 1, MODE_BVH = 2 };
+
+// fn(begin, end) over [0, n) in contiguous chunks on up to 16 host threads
+template <class F>
+void parallelFor(size_t n, size_t min_chunk, F fn) {
+    if (n < 2 * min_chunk) { fn((size_t)0, n); return; }
+    static const size_t hw = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    const size_t threads = std::min(hw, n / min_chunk);
+    if (threads <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + threads - 1) / threads;
+    for (size_t t = 1; t < threads; t++) th.emplace_back([=] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+    fn((size_t)0, std::min(n, chunk));
+    for (auto &t : th) t.join();
+}
+
+// ZRT_TIMING=1 in the environment prints the host-side phases of a BVH scene build to stderr
+struct BuildLap {
+    bool on = std::getenv("ZRT_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void operator()(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[zrt build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // ---- host-side flattened scene (zrt_flatten.cpp) ------------------------------------------------
 struct FlatBvh {
