@@ -65,10 +65,11 @@ template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
-    cudaError_t upload(const std::vector<T> &v) {
-        cudaError_t e = reserve(v.size());
-        if (e != cudaSuccess || v.empty()) return e;
-        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    cudaError_t upload(const std::vector<T> &v) { return upload(v.data(), v.size()); }
+    cudaError_t upload(const T *src, size_t count) {
+        cudaError_t e = reserve(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
     }
     cudaError_t reserve(size_t count) {
         if (count <= n) return cudaSuccess;
@@ -211,8 +212,10 @@ int uploadMaterials(zrt_scene *sc) {
     std::vector<DevMaterial> mats(hs.materials.size());
     sc->d_texels.resize(hs.textures.size());
     for (size_t i = 0; i < hs.textures.size(); i++) {
-        if (hs.textures[i].kind != ZRT_TEXTURE_IMAGE) continue;
-        CUDA_TRY(sc->d_texels[i].upload(hs.texels[i]));
+        const zrt_texture &t = hs.textures[i];
+        if (t.kind != ZRT_TEXTURE_IMAGE) continue;
+        // straight from the caller's pixels (page-locked or not): a device scene keeps no host copy of the texels
+        CUDA_TRY(sc->d_texels[i].upload(t.pixels, (size_t)t.width * t.height * t.channels));
     }
     for (size_t i = 0; i < mats.size(); i++) {
         const zrt_material &m = hs.materials[i];
@@ -295,7 +298,7 @@ int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
     CUDA_TRY(r.spheres.upload(r.h_spheres));
     CUDA_TRY(r.triA.upload(A)); CUDA_TRY(r.triE1.upload(E1)); CUDA_TRY(r.triE2.upload(E2));
     CUDA_TRY(r.triMeta.upload(meta));
-    CUDA_TRY(r.nodes.upload(r.info.nodes));
+    CUDA_TRY(r.nodes.upload(r.info.nodes.data(), r.info.nodes.size()));
     lap("upload");
     r.ready = true;
     return ZRT_OK;
@@ -513,7 +516,7 @@ int zrt_scene_create(const zrt_scene_desc *desc, int device, zrt_scene **out) {
         hs.materials.assign(desc->materials, desc->materials + desc->n_materials);
         hs.textures.assign(desc->textures, desc->textures + desc->n_textures);
         hs.texels.resize(desc->n_textures);
-        for (uint32_t i = 0; i < desc->n_textures; i++) {
+        for (uint32_t i = 0; i < desc->n_textures && device < 0; i++) { // host-only scenes own a copy of the texels
             zrt_texture &t = hs.textures[i];
             if (t.kind != ZRT_TEXTURE_IMAGE) continue;
             const size_t bytes = (size_t)t.width * t.height * t.channels;
@@ -537,6 +540,7 @@ int zrt_scene_create(const zrt_scene_desc *desc, int device, zrt_scene **out) {
             return fail(ZRT_ERR_CUDA, "device setup failed: " + msg);
         }
         rc = uploadMaterials(sc);
+        for (auto &t : sc->host.textures) t.pixels = nullptr; // borrowed from the caller for the upload only
         if (rc != ZRT_OK) {
             zrt_scene_destroy(sc);
             return rc;

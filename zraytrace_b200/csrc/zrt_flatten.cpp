@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <thread>
 #if defined(__SSE__)
@@ -59,6 +60,20 @@ inline float boxScore(const Box &b) { // aabb.zig:99-105: 2*(dx^2+dy^2+dz^2), no
     return 2 * (dx * dx + dy * dy + dz * dz);
 }
 
+// Array whose elements start uninitialised: a std::vector would zero tens of MB on one thread (and fault the pages in
+// there) before the parallel passes that fill them.
+template <class T>
+struct Raw {
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void alloc(size_t count) { p.reset(new T[count]); n = count; }
+    size_t size() const { return n; }
+    T *data() { return p.get(); }
+    const T *data() const { return p.get(); }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
 struct RefNode {          // one bvh.zig BVHNode
     Box box;
     int32_t left, right;  // >= 0 node index, < 0: ~surface id (a surface referenced directly)
@@ -66,9 +81,9 @@ struct RefNode {          // one bvh.zig BVHNode
 
 struct RefTree {
     const HostScene &sc;
-    std::vector<Box> sbox;            // per surface: aabb min/max
-    std::vector<float> smid[3];       // per surface: aabb midpoint (the sort key, bvh.zig:38-48)
-    std::vector<RefNode> nodes;             // preallocated (< 2n nodes); slots handed out atomically
+    Raw<Box> sbox;            // per surface: aabb min/max
+    Raw<float> smid[3];       // per surface: aabb midpoint (the sort key, bvh.zig:38-48)
+    Raw<RefNode> nodes;       // preallocated (< 2n nodes); slots handed out atomically
     std::atomic<uint32_t> n_nodes{0};
     std::atomic<uint32_t> max_depth{0};
     // The two halves of a split are independent (disjoint sub-ranges of the id array, nodes allocated
@@ -79,9 +94,9 @@ struct RefTree {
 
     explicit RefTree(const HostScene &s) : sc(s) {
         const size_t n = sc.surfaces.size();
-        nodes.resize(2 * n + 2);
-        sbox.resize(n);
-        for (auto &m : smid) m.resize(n);
+        nodes.alloc(2 * n + 2);
+        sbox.alloc(n);
+        for (auto &m : smid) m.alloc(n);
         parallelFor(n, 16384, [this](size_t begin, size_t end) { for (size_t i = begin; i < end; i++) {
             Box b{};
             if (sc.surfaces[i].kind == ZRT_SURFACE_SPHERE) { // sphere.zig:24-29
@@ -214,20 +229,40 @@ struct RefTree {
         nodes[i] = RefNode{boxUnion(childBox(left), childBox(right)), left, right};
         return (int32_t)i;
     }
-    int32_t divide(uint32_t *ids, size_t n, uint32_t depth) { // bvh.zig:129-160
+    // Slot numbers (position in left-first DFS order, the tie-break key of bvh.zig:193-204) fall out of the build: a
+    // subtree over n surfaces owns the n slots from `base` on, its left half the first `split` of them.
+    // So does the pruning (aabb.zig:121): node boxes are exact unions, hence nested, so a box that is flat
+    // on an axis makes every box below it flat on that axis; conversely, if the node that references a surface
+    // directly has a box with thickness, so do all its ancestors and the reference reaches the surface.
+    std::vector<uint32_t> slot_surface, slot_of; // slot -> surface id, surface id -> slot
+    std::vector<uint8_t> slot_visible;           // slot -> 0 if the surface sits under a zero-thickness box
+    void leafSlot(size_t slot, uint32_t surface, bool visible) {
+        slot_surface[slot] = surface;
+        slot_of[surface] = (uint32_t)slot;
+        slot_visible[slot] = visible ? 1 : 0;
+    }
+    int32_t divide(uint32_t *ids, size_t n, uint32_t depth, size_t base) { // bvh.zig:129-160
         uint32_t seen = max_depth.load();
         while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
-        if (n == 1) return create(~(int32_t)ids[0], ~(int32_t)ids[0]);
-        if (n == 2) return create(~(int32_t)ids[1], ~(int32_t)ids[0]);
+        if (n == 1) {
+            leafSlot(base, ids[0], !boxFlat(sbox[ids[0]]));
+            return create(~(int32_t)ids[0], ~(int32_t)ids[0]);
+        }
+        if (n == 2) { // left child = surfaces[1]
+            const bool visible = !boxFlat(boxUnion(sbox[ids[1]], sbox[ids[0]]));
+            leafSlot(base, ids[1], visible);
+            leafSlot(base + 1, ids[0], visible);
+            return create(~(int32_t)ids[1], ~(int32_t)ids[0]);
+        }
         const size_t split = optimalAxisDivide(ids, n);
         int32_t l, r;
         if (depth <= kParallelDepth && n >= kParallelMin) {
-            std::thread left([&] { l = divide(ids, split, depth + 1); });
-            r = divide(ids + split, n - split, depth + 1);
+            std::thread left([&] { l = divide(ids, split, depth + 1, base); });
+            r = divide(ids + split, n - split, depth + 1, base + split);
             left.join();
         } else {
-            l = divide(ids, split, depth + 1);
-            r = divide(ids + split, n - split, depth + 1);
+            l = divide(ids, split, depth + 1, base);
+            r = divide(ids + split, n - split, depth + 1, base + split);
         }
         return create(l, r);
     }
@@ -337,7 +372,7 @@ struct RefTree {
         if (n < kLiteralBelow) {
             uint32_t ids[kLiteralBelow];
             std::memcpy(ids, ord[parent_final].data() + lo, n * sizeof(uint32_t));
-            return divide(ids, n, depth);
+            return divide(ids, n, depth, lo);
         }
         uint32_t seen = max_depth.load();
         while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
@@ -385,11 +420,14 @@ struct RefTree {
     }
     int32_t build(std::vector<uint32_t> *ids, bool literal) {
         const size_t n = ids->size();
+        slot_surface.resize(n);
+        slot_of.resize(n);
+        slot_visible.resize(n);
         if (!literal && n >= kPresortMin) return buildPresorted();
         ids_base = ids->data();
         scratch_a.resize(n);
         scratch_b.resize(n);
-        const int32_t root = divide(ids->data(), n, 1); // bvh.zig:171-185
+        const int32_t root = divide(ids->data(), n, 1, 0); // bvh.zig:171-185
         std::vector<uint64_t>().swap(scratch_a);
         std::vector<uint64_t>().swap(scratch_b);
         return root;
@@ -405,22 +443,8 @@ struct Flattener {
     const HostScene &sc;
     const RefTree &rt;
     FlatBvh *out;
-    std::vector<uint32_t> slot_of; // surface id -> slot (DFS first visit)
-    std::vector<uint32_t> sphere_seq; // surface id -> index into the BVH-mode device sphere array
-
-    void assignSlots(int32_t c) {
-        if (c < 0) {
-            const uint32_t s = (uint32_t)~c;
-            if (slot_of[s] == UINT32_MAX) {
-                slot_of[s] = (uint32_t)out->slot_surface.size();
-                out->slot_surface.push_back(s);
-                out->slot_visible.push_back(0);
-            }
-            return;
-        }
-        assignSlots(rt.nodes[c].left);
-        if (rt.nodes[c].right != rt.nodes[c].left) assignSlots(rt.nodes[c].right);
-    }
+    const std::vector<uint32_t> &slot_of; // surface id -> slot (DFS first visit), from the tree build
+    const std::vector<uint32_t> &sphere_seq; // surface id -> index into the BVH-mode device sphere array
     uint32_t leafRef(uint32_t surface) {
         out->slot_visible[slot_of[surface]] = 1;
         if (sc.surfaces[surface].kind == ZRT_SURFACE_SPHERE) return REF_LEAF | REF_SPHERE | sphere_seq[surface];
@@ -440,18 +464,6 @@ struct Flattener {
         else ok = survives(n.left) | survives(n.right);
         alive[c] = ok ? 1 : 0;
         return ok;
-    }
-    // precondition: survives(c).  emit() without the nodes: only marks the surfaces the reference can reach
-    // (all the SAH rebuild needs from the reference topology).
-    void markVisible(int32_t c) {
-        for (;;) {
-            if (c < 0) { leafRef((uint32_t)~c); return; }
-            const RefNode &n = rt.nodes[c];
-            if (n.left == n.right && n.left < 0) { leafRef((uint32_t)~n.left); return; }
-            const bool sl = survives(n.left), sr = survives(n.right);
-            if (sl && sr) markVisible(n.left);
-            c = sr ? n.right : n.left;
-        }
     }
     // precondition: survives(c)
     Emitted emit(int32_t c, uint32_t depth) {
@@ -479,15 +491,15 @@ struct Flattener {
 
 // ---- binned SAH rebuild over the surviving primitives (next-row component) ----
 struct SahBuilder {
-    const std::vector<Box> &pbox; // per primitive
-    const std::vector<uint32_t> &pref; // per primitive leaf ref
+    const Box *pbox;      // per primitive
+    const uint32_t *pref; // per primitive leaf ref
     // preallocated, one node per split.  A subtree over m primitives has exactly m - 1 nodes, so DFS pre-order
     // numbers (parent before its subtrees, left subtree contiguous: memory locality of the traversal, and a node order
     // that does not depend on thread timing) are known on the way down: left child = my + 1, right = my + |left|.
-    std::vector<DevNode> *nodes;
+    decltype(FlatBvh::nodes) *nodes;
     std::atomic<uint32_t> max_depth{0};
     std::atomic<uint32_t> spawned{0};
-    std::vector<float> cen[3];
+    Raw<float> cen[3];
 
     static float area(const Box &b) {
         const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
@@ -646,15 +658,11 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
     out->ref_nodes = rt.n_nodes.load();
     out->ref_max_depth = rt.max_depth.load();
 
-    Flattener fl{scene, rt, out, std::vector<uint32_t>(n, UINT32_MAX), std::vector<uint32_t>(n, 0),
-                 std::vector<int8_t>(rt.n_nodes.load(), -1)};
+    out->slot_surface.swap(rt.slot_surface);
+    std::vector<uint32_t> sphere_seq(n, 0); // surface id -> index into the BVH-mode device sphere array
     uint32_t nsph = 0;
     for (size_t i = 0; i < n; i++)
-        if (scene.surfaces[i].kind == ZRT_SURFACE_SPHERE) fl.sphere_seq[i] = nsph++;
-    out->slot_surface.reserve(n);
-    out->slot_visible.reserve(n);
-    fl.assignSlots(root);
-    lap("slots");
+        if (scene.surfaces[i].kind == ZRT_SURFACE_SPHERE) sphere_seq[i] = nsph++;
     auto countLeaves = [&] {
         out->leaves = out->pruned = 0;
         for (uint8_t v : out->slot_visible) {
@@ -662,40 +670,43 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
             out->pruned += !v;
         }
     };
-    const bool any = fl.survives(root);
-    if (sah && any) {
-        fl.markVisible(root);
+    if (sah) { // the SAH rebuild needs only the set of reachable surfaces from the reference topology
+        out->slot_visible.swap(rt.slot_visible);
         countLeaves();
     }
     if (!sah || out->leaves <= 1) { // the reference topology itself (also when there is nothing to re-split)
+        Flattener fl{scene, rt, out, rt.slot_of, sphere_seq, std::vector<int8_t>(rt.n_nodes.load(), -1)};
+        out->slot_visible.assign(n, 0); // emit() marks what it reaches
         out->nodes.reserve(n);
-        out->root = any ? fl.emit(root, 1).ref : REF_EMPTY;
+        out->root = fl.survives(root) ? fl.emit(root, 1).ref : REF_EMPTY;
         countLeaves();
     }
     lap("slots + flatten");
     if (sah && out->leaves > 1) {
-        std::vector<Box> pbox;
-        std::vector<uint32_t> pref;
-        pbox.reserve(out->leaves);
-        pref.reserve(out->leaves);
-        for (size_t s = 0; s < out->slot_surface.size(); s++) {
-            if (!out->slot_visible[s]) continue;
-            const uint32_t surf = out->slot_surface[s];
-            pbox.push_back(rt.sbox[surf]);
-            pref.push_back(scene.surfaces[surf].kind == ZRT_SURFACE_SPHERE ? (REF_LEAF | REF_SPHERE | fl.sphere_seq[surf])
-                                                                           : (REF_LEAF | (uint32_t)s));
-        }
+        std::vector<uint32_t> vis; // the visible slots, in slot order
+        vis.reserve(out->leaves);
+        for (size_t s = 0; s < out->slot_surface.size(); s++)
+            if (out->slot_visible[s]) vis.push_back((uint32_t)s);
+        const size_t m = vis.size();
+        Raw<Box> pbox;
+        Raw<uint32_t> pref, pid;
+        pbox.alloc(m); pref.alloc(m); pid.alloc(m);
         out->nodes.clear();
-        out->nodes.resize(pbox.size() - 1);
-        SahBuilder sb{pbox, pref, &out->nodes, {}, {}, {}};
-        for (int k = 0; k < 3; k++) {
-            sb.cen[k].resize(pbox.size());
-            for (size_t i = 0; i < pbox.size(); i++) sb.cen[k][i] = 0.5f * (pbox[i].mn[k] + pbox[i].mx[k]);
-        }
-        std::vector<uint32_t> pid(pbox.size());
-        for (size_t i = 0; i < pid.size(); i++) pid[i] = (uint32_t)i;
+        out->nodes.resize(m - 1);
+        SahBuilder sb{pbox.data(), pref.data(), &out->nodes, {}, {}, {}};
+        for (int k = 0; k < 3; k++) sb.cen[k].alloc(m);
+        parallelFor(m, 16384, [&](size_t begin, size_t end) {
+            for (size_t i = begin; i < end; i++) {
+                const uint32_t s = vis[i], surf = out->slot_surface[s];
+                const Box &b = rt.sbox[surf];
+                pbox[i] = b;
+                pref[i] = scene.surfaces[surf].kind == ZRT_SURFACE_SPHERE ? (REF_LEAF | REF_SPHERE | sphere_seq[surf]) : (REF_LEAF | s);
+                for (int k = 0; k < 3; k++) sb.cen[k][i] = 0.5f * (b.mn[k] + b.mx[k]);
+                pid[i] = (uint32_t)i;
+            }
+        });
         lap("sah setup");
-        out->root = sb.build(pid.data(), pid.size(), 1, 0).ref;
+        out->root = sb.build(pid.data(), m, 1, 0).ref;
         out->max_depth = sb.max_depth.load();
         lap("sah build");
     }

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/zrt.h"
@@ -172,8 +173,17 @@ struct BuildLap {
 };
 
 // ---- host-side flattened scene (zrt_flatten.cpp) ------------------------------------------------
+// std::allocator whose value-less construct() default-initialises: resize() of a vector of plain structs then leaves the
+// new elements uninitialised instead of zeroing (and page-faulting) tens of MB on one thread
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+    template <class U> void construct(U *p) { ::new ((void *)p) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+};
+
 struct FlatBvh {
-    std::vector<DevNode> nodes;
+    std::vector<DevNode, DefaultInitAlloc<DevNode>> nodes;
     uint32_t root = REF_EMPTY;
     std::vector<uint32_t> slot_surface;  // slot -> surface id (DFS order of the reference tree)
     std::vector<uint8_t> slot_visible;   // 0 if pruned (under a zero-thickness box)

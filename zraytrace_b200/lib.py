@@ -85,9 +85,17 @@ class Scene:
     def __exit__(self, *a):
         self.close()
 
-    def render(self, camera, params):
-        """-> (image float32 [H][W][3] row 0 = bottom, Counters, Timing)   (raytrace.zig:136-203)"""
-        img = np.empty((params.height, params.width, 3), np.float32)
+    def render(self, camera, params, out=None):
+        """-> (image float32 [H][W][3] row 0 = bottom, Counters, Timing)   (raytrace.zig:136-203)
+        out: optional caller-owned C-contiguous float32 [H][W][3] host buffer (page-locked memory makes the
+        device-to-host copy one DMA instead of a staged copy into fresh pages)."""
+        shape = (params.height, params.width, 3)
+        if out is None:
+            img = np.empty(shape, np.float32)
+        else:
+            if out.dtype != np.float32 or out.shape != shape or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"out must be a C-contiguous float32 array of shape {shape}")
+            img = out
         cnt, tm = A.Counters(), A.Timing()
         _check(lib().zrt_render(self._h, C.byref(camera), C.byref(params), img.ctypes.data, C.byref(cnt), C.byref(tm)))
         return img, cnt, tm
