@@ -265,14 +265,14 @@ def run_zrt(args, wl_name, wl):
     e2e_times = []
     h2d = hs.upload_bytes() + 256
     d2h = wl["w"] * wl["h"] * 12 + 48
-    pinned = torch.empty((wl["h"], wl["w"], 3), dtype=torch.float32).pin_memory()  # the caller's result buffer
-    pinned_np = pinned.numpy()
+    pinned = torch.empty((wl["h"], wl["w"], 3), dtype=torch.float32).pin_memory() if world > 1 else None
+    host_image = Z.HostImage((wl["h"], wl["w"], 3)) if world == 1 else None  # the caller's result image (zrt_pinned_alloc)
     for i in range(2 + min(args.steps, 3)):
         barrier()
         t0 = time.perf_counter()
         if world == 1:
             with Z.Scene(hs, device=local_rank) as sc2:  # zrt_scene_create: flatten + H2D
-                img, c_e2e, _ = sc2.render(hs.camera, params, out=pinned_np)  # zrt_render: kernels + D2H into the host buffer
+                img, c_e2e, _ = sc2.render(hs.camera, params, out=host_image.array)  # zrt_render: kernels + D2H into the host buffer
         else:
             with Z.Scene(hs, device=local_rank) as sc2:
                 a2, c2 = D.render_distributed(sc2, hs.camera, params)

@@ -177,6 +177,14 @@ void zrt_scene_destroy(zrt_scene *scene);
 int zrt_render(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
                float *out_rgb, zrt_counters *counters, zrt_timing *timing);
 
+/* Page-locked host memory for the image that zrt_render / zrt_render_rgb8 / zrt_primary_hits fill (what the reference
+ * takes from its allocator in Image.init, image.zig:74-84): the copy back is then one DMA instead of a staged copy
+ * through the driver's bounce buffer into pages the host touches for the first time (41.4 instead of 44.4 ms end to
+ * end on the 12 MB headline image).  Any host pointer works with the render calls; these two are for hosts that do
+ * not link the CUDA runtime themselves.  zrt_pinned_free(NULL) is a no-op. */
+int zrt_pinned_alloc(size_t bytes, void **out);
+void zrt_pinned_free(void *ptr);
+
 /* raytrace.render() + the quantisation of png_image.writeFile (png_image.zig:131-142) fused on the device:
  * out_rgb8 is width*height*3 bytes, u8 = clamp(255.999 * c, 0, 255) truncated, row 0 = TOP scanline (the order
  * a PNG stores).  Moves a quarter of the bytes of zrt_render back to the host; the bytes are identical to

@@ -308,3 +308,23 @@ def test_device_output_stage_matches_host_quantisation(built, tmp_path):
     host.png_write(a, img_f)
     host.png_write_rgb8(b, img_8)
     assert np.array_equal(np.array(Image.open(a)), np.array(Image.open(b)))
+
+
+def test_render_into_page_locked_host_image(built):
+    """zrt_pinned_alloc: the caller's result image in page-locked memory (what bench.py's end-to-end arm passes).
+    Same bytes as the render into ordinary numpy memory, for the float and the 8-bit output stage; a buffer of the
+    wrong shape or dtype is refused before anything is launched."""
+    sc, cam, dev = built("three_balls")
+    p = A.make_params(96, 64, 16, 30, x_limit=A.ZRT_XLIMIT_WIDTH)
+    img, c, _ = dev.render(cam, p)
+    img8, c8, _ = dev.render_rgb8(cam, p)
+    with Z.HostImage((64, 96, 3)) as hf, Z.HostImage((64, 96, 3), np.uint8) as h8:
+        hf.array.fill(np.nan)
+        got, c2, _ = dev.render(cam, p, out=hf.array)
+        assert got is hf.array and np.array_equal(got, img) and c2.as_dict() == c.as_dict()
+        got8, c3, _ = dev.render_rgb8(cam, p, out=h8.array)
+        assert np.array_equal(got8, img8) and c3.as_dict() == c8.as_dict()
+        with pytest.raises(ValueError):
+            dev.render(cam, p, out=h8.array)
+        with pytest.raises(ValueError):
+            dev.render(cam, p, out=hf.array[:, ::2])

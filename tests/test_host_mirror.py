@@ -50,6 +50,20 @@ def test_no_cpu_fallback_without_device():
         assert e.value.code == A.ZRT_ERR_NO_DEVICE
 
 
+def test_host_alloc_needs_the_driver_and_checks_arguments():
+    """zrt_pinned_alloc page-locks through the CUDA driver: without a device it fails like every compute call, and
+    it never hands back a pointer on an error."""
+    p = C.c_void_p(1)
+    assert Z.lib().zrt_pinned_alloc(0, C.byref(p)) == A.ZRT_ERR_INVALID and not p.value
+    assert Z.lib().zrt_pinned_alloc(64, None) == A.ZRT_ERR_INVALID
+    Z.lib().zrt_pinned_free(None)
+    if Z.device_count() == 0:
+        p = C.c_void_p(1)
+        assert Z.lib().zrt_pinned_alloc(64, C.byref(p)) == A.ZRT_ERR_NO_DEVICE and not p.value
+        with pytest.raises(Z.ZrtError):
+            Z.HostImage((4, 4, 3))
+
+
 def test_invalid_scene_rejected():
     from zraytrace_b200.scene import SceneBuilder
     b = SceneBuilder()

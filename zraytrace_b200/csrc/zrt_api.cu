@@ -550,6 +550,19 @@ int zrt_scene_create(const zrt_scene_desc *desc, int device, zrt_scene **out) {
     return ZRT_OK;
 }
 
+int zrt_pinned_alloc(size_t bytes, void **out) {
+    if (!out) return fail(ZRT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return fail(ZRT_ERR_INVALID, "zero-sized allocation");
+    if (zrt_device_count() == 0) return fail(ZRT_ERR_NO_DEVICE, "no CUDA device visible: page-locking needs the driver");
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return ZRT_OK;
+}
+
+void zrt_pinned_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 void zrt_scene_destroy(zrt_scene *sc) {
     if (!sc) return;
     if (sc->device >= 0) {

@@ -45,6 +45,9 @@ def lib():
         L.zrt_trace_statistics.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), P(A.TraceStats)]
         L.zrt_selftest.argtypes = [C.c_int, P(C.c_uint64)]
         L.zrt_measure_peaks.argtypes = [C.c_int, P(C.c_double), C.c_int]
+        L.zrt_pinned_alloc.argtypes = [C.c_size_t, P(C.c_void_p)]
+        L.zrt_pinned_free.argtypes = [C.c_void_p]
+        L.zrt_pinned_free.restype = None
         _lib = L
     return _lib
 
@@ -56,6 +59,43 @@ def _check(rc):
 
 def device_count():
     return lib().zrt_device_count()
+
+
+class HostImage:
+    """Page-locked host buffer (`zrt_pinned_alloc`) seen as a numpy array: pass `.array` as `out=` to Scene.render /
+    render_rgb8 so the image comes back in one DMA.  The array is only valid until close()."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self._p = C.c_void_p()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        _check(lib().zrt_pinned_alloc(n, C.byref(self._p)))
+        self.array = np.frombuffer((C.c_char * n).from_address(self._p.value), dtype=dtype).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().zrt_pinned_free(self._p)
+            self._p = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _out_buffer(out, shape, dtype):
+    if out is None:
+        return np.empty(shape, dtype)
+    if out.dtype != dtype or out.shape != shape or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"out must be a C-contiguous {np.dtype(dtype).name} array of shape {shape}")
+    return out
 
 
 class Scene:
@@ -89,21 +129,15 @@ class Scene:
         """-> (image float32 [H][W][3] row 0 = bottom, Counters, Timing)   (raytrace.zig:136-203)
         out: optional caller-owned C-contiguous float32 [H][W][3] host buffer (page-locked memory makes the
         device-to-host copy one DMA instead of a staged copy into fresh pages)."""
-        shape = (params.height, params.width, 3)
-        if out is None:
-            img = np.empty(shape, np.float32)
-        else:
-            if out.dtype != np.float32 or out.shape != shape or not out.flags["C_CONTIGUOUS"]:
-                raise ValueError(f"out must be a C-contiguous float32 array of shape {shape}")
-            img = out
+        img = _out_buffer(out, (params.height, params.width, 3), np.float32)
         cnt, tm = A.Counters(), A.Timing()
         _check(lib().zrt_render(self._h, C.byref(camera), C.byref(params), img.ctypes.data, C.byref(cnt), C.byref(tm)))
         return img, cnt, tm
 
-    def render_rgb8(self, camera, params):
+    def render_rgb8(self, camera, params, out=None):
         """-> (uint8 [H][W][3] with row 0 = TOP scanline, quantised on the device like png_image.zig:136-140,
         Counters, Timing)"""
-        img = np.empty((params.height, params.width, 3), np.uint8)
+        img = _out_buffer(out, (params.height, params.width, 3), np.uint8)
         cnt, tm = A.Counters(), A.Timing()
         _check(lib().zrt_render_rgb8(self._h, C.byref(camera), C.byref(params), img.ctypes.data, C.byref(cnt), C.byref(tm)))
         return img, cnt, tm
