@@ -89,6 +89,62 @@ def test_obj_reader_matches_python_parser(name):  # obj_reader.zig:201-226
     assert len(got) == {"Man": 3933, "bunny": 4968, "teapot": 6320}[name]
 
 
+def _obj(tmp_path, text, name="m.obj"):
+    path = str(tmp_path / name)
+    with open(path, "wb") as f:
+        f.write(text.encode() if isinstance(text, str) else text)
+    return path
+
+
+def test_obj_reader_grammar_and_errors(tmp_path):
+    """obj_reader.zig:21-198 line by line: CRLF, `v/vt/vn` and `v//vn` faces, fans of 3..6 vertices, numbers the fast
+    parser hands to strtof, an unterminated last line (never returned by readUntilDelimiterAlloc), and every way the
+    reference's loop fails (`try`): bad numbers, 2 or 7 face vertices, an index beyond the vertices read so far."""
+    ok = ("# comment\r\nv 0 0 0\r\nv +1 0 0\nv 0 1e0 0 9 9\nv  0   0  0x1p0\nv 1 1 1\nv 2 2 2\nvn 0 0 1\nvt 0.5 0.5\n"
+          "f 1 2 3\nf 1/1/1 2/2/2 3/3/3 4/4/4\nf 1//1 2//2 3//3 4//4 5//5\nf 1/7 2/7 3/7 4/7 5/7 6/7\n"
+          "g ignored\nf 3 2 1")  # the last face has no newline: dropped
+    t = host.read_obj(_obj(tmp_path, ok))
+    v = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1), (2, 2, 2)], np.float32)
+    fans = [(0, 1, 2), (0, 1, 2), (2, 3, 0), (0, 1, 2), (2, 3, 0), (3, 4, 0), (0, 1, 2), (2, 3, 0), (3, 4, 0), (4, 5, 0)]
+    assert np.array_equal(t, v[np.array(fans)])
+    assert len(host.read_obj(_obj(tmp_path, ""))) == 0
+    bad = ["v 0 0\n", "v 0 0 zero\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3 1 2 3 1\n",
+           "v 0 0 0\nv 1 0 0\nf 1 2 3\nv 0 1 0\n",  # forward reference: only two vertices had been read
+           "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 0 1 2\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 -3\n",
+           "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1/x 2 3\n", "vn 0 0\n", "v 0 0 0 " + " " * 20001 + "\n"]
+    for text in bad:
+        with pytest.raises(Z.ZrtError) as e:
+            host.read_obj(_obj(tmp_path, text))
+        assert e.value.code == A.ZRT_ERR_INVALID, text[:40]
+    with pytest.raises(Z.ZrtError) as e:
+        host.read_obj(str(tmp_path / "missing.obj"))
+    assert e.value.code == A.ZRT_ERR_IO
+
+
+def test_obj_reader_parallel_chunks_keep_file_order(tmp_path):
+    """A file large enough to be parsed by several chunks on separate threads: vertices and faces interleaved, faces
+    that refer far back, and one that refers one vertex too far ahead (an error only because of where it stands)."""
+    rng = np.random.default_rng(7)
+    n = 60000
+    verts = rng.standard_normal((n, 3)).astype(np.float32)
+    lines, tris = [], []
+    for i in range(n):
+        lines.append("v %r %r %r" % tuple(float(x) for x in verts[i]))
+        if i >= 2:
+            a, b = int(rng.integers(0, i + 1)), int(rng.integers(0, i + 1))
+            lines.append(f"f {i + 1} {a + 1}/1 {b + 1}//2")
+            tris.append((i, a, b))
+    text = "\n".join(lines) + "\n"
+    assert len(text) > 4 * (256 << 10)
+    got = host.read_obj(_obj(tmp_path, text))
+    assert np.array_equal(got, verts[np.array(tris)])
+    k = len(lines) * 3 // 4
+    lines.insert(k, f"f 1 2 {sum(1 for x in lines[:k] if x[0] == 'v') + 1}")
+    with pytest.raises(Z.ZrtError) as e:
+        host.read_obj(_obj(tmp_path, "\n".join(lines) + "\n"))
+    assert e.value.code == A.ZRT_ERR_INVALID
+
+
 @pytest.mark.parametrize("name", ["earthmap.png", "nitor-logo-25.png"])
 def test_png_reader_matches_pil(name):  # png_image.zig:19-94 incl. the row flip
     got = host.png_read(os.path.join(host.ASSETS, "images", name))
