@@ -255,10 +255,12 @@ def _tie_heavy_scene(seed, n_tris, n_spheres):
     return b.build()
 
 
-@pytest.mark.parametrize("seed,n_tris,n_spheres", [(1, 2500, 40), (2, 6000, 0), (3, 2100, 300)])
+@pytest.mark.parametrize("seed,n_tris,n_spheres", [(1, 2500, 40), (2, 6000, 0), (3, 2100, 300), (4, 300, 20), (5, 11, 0),
+                                                   (6, 9, 2), (7, 2040, 7)])  # > 10 surfaces: raytrace.zig:111-133
 def test_presorted_tree_build_matches_oracle_on_tie_heavy_scenes(seed, n_tris, n_spheres):
-    """Above 2048 surfaces the reference tree is rebuilt from five presorted index lists instead of by sorting
-    inside the recursion (zrt_flatten.cpp); the oracle's pointer tree sorts literally like bvh.zig:71-120."""
+    """From 2048 surfaces on the reference tree is rebuilt from five presorted index lists instead of by sorting
+    inside the recursion (zrt_flatten.cpp), below that literally; either way slots and pruning are assigned where
+    the leaves are created.  The oracle's pointer tree sorts like bvh.zig:71-120 and walks the tree for both."""
     sc = _tie_heavy_scene(seed, n_tris, n_spheres)
     o_order, o_vis, st = zro_py.bvh_order(sc)
     with Z.Scene(sc, device=-1) as hs:
@@ -266,7 +268,9 @@ def test_presorted_tree_build_matches_oracle_on_tie_heavy_scenes(seed, n_tris, n
         info = hs.bvh_info(A.ZRT_FLAG_BVH_REFERENCE)
     assert np.array_equal(o_order, z_order) and np.array_equal(o_vis, z_vis)
     assert info.reference_nodes == st.bvh_nodes and info.reference_max_depth == st.bvh_max_depth
-    assert (~o_vis).sum() > 0
+    assert info.leaves == int(o_vis.sum()) and info.pruned_surfaces == int((~o_vis).sum())
+    if n_tris >= 300:
+        assert (~o_vis).sum() > 0
 
 
 def test_presorted_tree_build_matches_literal_build_on_config4(monkeypatch):
