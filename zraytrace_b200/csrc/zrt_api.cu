@@ -347,19 +347,24 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.s_begin = sb; P.s_end = se;
     plan->n_samples = se - sb;
     const uint64_t pixels = (uint64_t)P.x_end * P.height;
-    // L slices per pixel (see k_trace).  Sphere lists: 8 measured best on C5 at 125..1000 spp (items of 16..125
-    // samples), more only when the image is so small that 8 would leave resident warps without items (~1.2 M items
-    // wanted).  BVH / surface-list scenes: 32, i.e. the 32 lanes of a warp trace 32 slices of ONE pixel, so their
-    // primary rays walk the same nodes (measured against 8: C2 13.2 -> 11.0 ms, C3 36.0 -> 34.2, C4 119 -> 101).
+    // L slices per pixel (see k_trace).  Two costs pull in opposite directions: every item costs ~68 warp instructions
+    // to hand over (fewer, longer items are cheaper), and the launch cannot end before its longest item, which sits on
+    // the most expensive pixels (glass: ~7x the average rays per sample), so items must stay a small fraction of the
+    // launch: L ~ 54 x resident lanes / pixels, independent of the sample count.  Measured on the 7-spheres scene
+    // (best L): 2000^2 -> 2 (16.96 ms against 18.12 with 8), 1400^2 -> 4, 1000^2 -> 8 at 125..1000 spp, 600^2 -> 16,
+    // 500^2 and below -> 32.  BVH / surface-list scenes: 32, i.e. the 32 lanes of a warp trace 32 slices of ONE pixel,
+    // so their primary rays walk the same nodes (measured against 8: C2 13.2 -> 11.0 ms, C3 36.0 -> 34.2, C4 119 -> 101).
     // The caller can pin it (sample_chunks = 1 reproduces the reference's sequential f32 sum per pixel).
     uint32_t lanes = p->sample_chunks;
     if (lanes == 0) {
-        const uint32_t by_samples = (r->mode == MODE_SPHERES) ? 8u : 32u;
-        const uint64_t by_items = (1200000ull + pixels - 1) / (pixels ? pixels : 1);
-        lanes = (uint32_t)(by_samples > by_items ? by_samples : by_items);
-        uint32_t p2 = 1;
-        while (p2 < lanes && p2 < 32u) p2 <<= 1; // round up to a power of two
-        lanes = p2;
+        lanes = 32u;
+        if (r->mode == MODE_SPHERES) {
+            static int sms = 0;
+            if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device) != cudaSuccess) sms = 148;
+            const double target = 54.0 * 1024.0 * (double)sms / (double)(pixels ? pixels : 1); // 8 blocks x 128 lanes per SM
+            lanes = 1u;
+            while (lanes < 32u && (double)lanes * 1.41421356 < target) lanes <<= 1; // nearest power of two
+        }
     }
     if (lanes > 32u) lanes = 32u;
     if (p->sample_chunks == 0) // the slice buffer is lanes x 12 B per pixel: keep the automatic choice under 2 GiB
