@@ -200,7 +200,7 @@ def run_zrt(args, wl_name, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0))
+    hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0)).pin()  # page-locked texels
     flags = A.ZRT_FLAG_BVH_REFERENCE if args.reftree else 0
     params = params_for(wl, flags=flags)
     scene = Z.Scene(hs, device=local_rank)
@@ -304,7 +304,7 @@ def run_zrt(args, wl_name, wl):
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": rays_per_step / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
-                    "path": "zrt_scene_create (pageable scene arrays, H2D) + zrt_render into a page-locked host image (D2H) per step" if world == 1 else
+                    "path": "zrt_scene_create (H2D: page-locked texels, pageable primitive arrays) + zrt_render into a page-locked host image (D2H) per step" if world == 1 else
                             "zrt_scene_create + zrt_render_device + NCCL reduce + D2H per step"},
             "published_reference": {"value": 3.47, "unit": "Mrays/s", "note": "README.md:49-61, unknown CPU, 1 thread"}}
     cpu = None

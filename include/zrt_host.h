@@ -50,6 +50,10 @@ int zrt_host_scene_load(uint32_t scene_index, const char *assets_dir, uint32_t v
 const zrt_scene_desc *zrt_host_scene_desc(const zrt_host_scene *scene);
 const zrt_camera *zrt_host_scene_camera(const zrt_host_scene *scene);
 void zrt_host_scene_free(zrt_host_scene *scene);
+/* Move the scene's texel arrays into page-locked memory (zrt_pinned_alloc) on the calling thread's current device, so
+ * that every later zrt_scene_create uploads them with one DMA each.  Needs a device (ZRT_ERR_NO_DEVICE otherwise, the
+ * scene is left as it was); the description returned by zrt_host_scene_desc stays valid. */
+int zrt_host_scene_pin(zrt_host_scene *scene);
 
 /* scenes.render_scene (scenes.zig:267-277) followed by nothing else: build scene `scene_index`, render
  * it on `device` through zrt_render, return image and counters. */

@@ -328,3 +328,17 @@ def test_render_into_page_locked_host_image(built):
             dev.render(cam, p, out=h8.array)
         with pytest.raises(ValueError):
             dev.render(cam, p, out=hf.array[:, ::2])
+
+
+def test_scene_with_page_locked_texels_renders_the_same_image():
+    """zrt_host_scene_pin moves the texel arrays into page-locked memory; nothing about the render changes."""
+    from zraytrace_b200 import host
+    p = A.make_params(80, 60, 8, 30, x_limit=A.ZRT_XLIMIT_WIDTH)
+    hs = host.HostScene(host.SCENE_THREE_BALLS)
+    with Z.Scene(hs, device=0) as dev:
+        img1, c1, _ = dev.render(hs.camera, p)
+    hs.pin()
+    with Z.Scene(hs, device=0) as dev:
+        img2, c2, _ = dev.render(hs.camera, p)
+    hs.close()
+    assert np.array_equal(img1, img2) and c1.as_dict() == c2.as_dict()

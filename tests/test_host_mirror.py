@@ -64,6 +64,23 @@ def test_host_alloc_needs_the_driver_and_checks_arguments():
             Z.HostImage((4, 4, 3))
 
 
+def test_host_scene_pin_without_a_device_leaves_the_scene_alone():
+    hs = host.HostScene(host.SCENE_THREE_BALLS)
+    before = [bytes(C.string_at(hs.desc.textures[i].pixels, 64)) for i in range(hs.desc.n_textures)
+              if hs.desc.textures[i].kind == A.ZRT_TEXTURE_IMAGE]
+    assert len(before) == 2
+    if Z.device_count() == 0:
+        with pytest.raises(Z.ZrtError) as e:
+            hs.pin()
+        assert e.value.code == A.ZRT_ERR_NO_DEVICE
+    else:
+        hs.pin().pin()  # idempotent
+    after = [bytes(C.string_at(hs.desc.textures[i].pixels, 64)) for i in range(hs.desc.n_textures)
+             if hs.desc.textures[i].kind == A.ZRT_TEXTURE_IMAGE]
+    assert before == after
+    hs.close()
+
+
 def test_invalid_scene_rejected():
     from zraytrace_b200.scene import SceneBuilder
     b = SceneBuilder()

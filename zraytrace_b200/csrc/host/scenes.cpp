@@ -9,6 +9,9 @@
 
 #include <sys/stat.h>
 
+#include <algorithm>
+#include <cstring>
+
 #include "../../../include/zrt_host.h"
 
 struct zrt_host_scene {
@@ -18,10 +21,12 @@ struct zrt_host_scene {
     std::vector<zrt_material> materials;
     std::vector<zrt_texture> textures;
     std::vector<uint8_t *> owned_pixels;
+    std::vector<uint8_t *> pinned_pixels; // after zrt_host_scene_pin
     zrt_scene_desc desc{};
     zrt_camera camera{};
     ~zrt_host_scene() {
         for (uint8_t *p : owned_pixels) zrt_host_free(p);
+        for (uint8_t *p : pinned_pixels) zrt_pinned_free(p);
     }
 };
 
@@ -272,6 +277,27 @@ int zrt_host_scene_load(uint32_t scene_index, const char *assets_dir, uint32_t v
 const zrt_scene_desc *zrt_host_scene_desc(const zrt_host_scene *scene) { return scene ? &scene->desc : nullptr; }
 const zrt_camera *zrt_host_scene_camera(const zrt_host_scene *scene) { return scene ? &scene->camera : nullptr; }
 void zrt_host_scene_free(zrt_host_scene *scene) { delete scene; }
+
+int zrt_host_scene_pin(zrt_host_scene *scene) {
+    if (!scene) return ZRT_ERR_INVALID;
+    for (zrt_texture &t : scene->textures) {
+        if (t.kind != ZRT_TEXTURE_IMAGE || !t.pixels) continue;
+        if (std::find(scene->pinned_pixels.begin(), scene->pinned_pixels.end(), t.pixels) != scene->pinned_pixels.end()) continue;
+        const size_t bytes = (size_t)t.width * t.height * t.channels;
+        void *locked = nullptr;
+        const int rc = zrt_pinned_alloc(bytes, &locked);
+        if (rc != ZRT_OK) return rc;
+        std::memcpy(locked, t.pixels, bytes);
+        auto it = std::find(scene->owned_pixels.begin(), scene->owned_pixels.end(), t.pixels);
+        if (it != scene->owned_pixels.end()) {
+            zrt_host_free(*it);
+            scene->owned_pixels.erase(it);
+        }
+        t.pixels = (const uint8_t *)locked;
+        scene->pinned_pixels.push_back((uint8_t *)locked);
+    }
+    return ZRT_OK;
+}
 
 int zrt_host_render_scene(uint32_t scene_index, const char *assets_dir, uint32_t variant, const zrt_params *params,
                           int device, float *out_rgb, zrt_counters *counters, zrt_timing *timing) { // scenes.zig:267-277

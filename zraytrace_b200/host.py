@@ -36,6 +36,7 @@ def _L():
         L.zrt_host_scene_camera.restype = P(A.Camera)
         L.zrt_host_scene_free.argtypes = [C.c_void_p]
         L.zrt_host_scene_free.restype = None
+        L.zrt_host_scene_pin.argtypes = [C.c_void_p]
         L.zrt_host_render_scene.argtypes = [C.c_uint32, C.c_char_p, C.c_uint32, P(A.Params), C.c_int, C.c_void_p,
                                             P(A.Counters), P(A.Timing)]
         _ready = True
@@ -107,6 +108,11 @@ class HostScene:
             self.close()
         except Exception:
             pass
+
+    def pin(self):
+        """Page-lock the texel arrays (zrt_host_scene_pin): scene uploads become one DMA per texture."""
+        _check(_L().zrt_host_scene_pin(self._h), "scene pin")
+        return self
 
     def upload_bytes(self):
         """host->device bytes zrt_scene_create moves for this scene (texels + primitives + materials)."""
