@@ -54,7 +54,7 @@ def algorithmic_ops(stats, counters):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_trace launch at the bench size, from the committed
 # `ncu --set full` capture named here (a number measured under a profiler is only ever used for this field)
-NCU_TRAFFIC = {"c5": {"bytes": 4141824 + 45649664, "source": "profiles/r1_v8_c5_k_trace.txt (1 GPU, 1000 spp)"}}
+NCU_TRAFFIC = {"c5": {"bytes": 3894528 + 44411136, "source": "profiles/r1_v10_c5_k_trace.txt (1 GPU, 1000 spp)"}}
 
 
 class ClockSampler:

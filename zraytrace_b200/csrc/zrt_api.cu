@@ -16,7 +16,7 @@
 #include "zrt_internal.h"
 
 namespace zrt {
-void launch_trace(const KParams &P, int mode, cudaStream_t st);
+uint32_t launch_trace(const KParams &P, int mode, cudaStream_t st);
 void launch_primary(const KParams &P, int mode, cudaStream_t st);
 void launch_resolve(const float *part, float *out, uint32_t n, uint32_t chunks, float scale, cudaStream_t st);
 void launch_resolve_rgb8(const float *part, uint8_t *out, uint32_t width, uint32_t height, uint32_t chunks, float scale,
@@ -452,8 +452,7 @@ int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d
     if (e_k0) CUDA_TRY(cudaEventRecord(e_k0, st));
     bool traced = false;
     if (plan.n_samples > 0 && P.max_depth > 0) {
-        launch_trace(P, plan.mode, st);
-        (*launches)++;
+        *launches += launch_trace(P, plan.mode, st); // k_trace (+ k_finish_counters)
         traced = true;
     } else {
         // no samples, or max_depth = 0: every sample ends at the recursion limit without casting a ray
