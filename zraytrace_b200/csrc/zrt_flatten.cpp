@@ -74,6 +74,17 @@ struct Raw {
     const T &operator[](size_t i) const { return p[i]; }
 };
 
+// f() on its own thread, or in line when a thread would cost more than the work
+struct Maybe {
+    std::thread t;
+    template <class F>
+    Maybe(bool threaded, F f) {
+        if (threaded) t = std::thread(f);
+        else f();
+    }
+    void join() { if (t.joinable()) t.join(); }
+};
+
 struct RefNode {          // one bvh.zig BVHNode
     Box box;
     int32_t left, right;  // >= 0 node index, < 0: ~surface id (a surface referenced directly)
@@ -391,17 +402,19 @@ struct RefTree {
                 base[axis] = idx;
                 sortAxis(axis, base[axis].data(), n, sa.data(), sb.data());
             };
-            std::thread ty([&] {
+            // a thread costs more than sorting a few thousand keys: small scenes do the ten steps in line
+            const bool mt = n >= 32768;
+            Maybe ty(mt, [&] {
                 sortBase(1);
-                std::thread t1([&] { refineRuns(base[1], 1, 2, 0, &ord[O_YZX]); });
-                std::thread t2([&] { refineRuns(base[1], 1, 0, -1, &root_y); }); // (y, x, idx): the root's y sort
+                Maybe t1(mt, [&] { refineRuns(base[1], 1, 2, 0, &ord[O_YZX]); });
+                Maybe t2(mt, [&] { refineRuns(base[1], 1, 0, -1, &root_y); }); // (y, x, idx): the root's y sort
                 refineRuns(base[1], 1, 0, 2, &ord[O_YXZ]);
                 t1.join();
                 t2.join();
             });
-            std::thread tz([&] { sortBase(2); refineRuns(base[2], 2, 1, 0, &ord[O_ZYX]); });
+            Maybe tz(mt, [&] { sortBase(2); refineRuns(base[2], 2, 1, 0, &ord[O_ZYX]); });
             sortBase(0);
-            std::thread tx([&] { refineRuns(base[0], 0, 1, 2, &ord[O_XYZ]); });
+            Maybe tx(mt, [&] { refineRuns(base[0], 0, 1, 2, &ord[O_XYZ]); });
             refineRuns(base[0], 0, 2, 1, &ord[O_XZY]);
             tx.join();
             ty.join();
@@ -505,10 +518,8 @@ struct SahBuilder {
         const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
         return 2.0f * (dx * dy + dy * dz + dz * dx);
     }
-    Emitted build(uint32_t *ids, size_t n, uint32_t depth, uint32_t my) {
-        if (n == 1) return Emitted{pref[ids[0]], pbox[ids[0]]};
-        uint32_t seen = max_depth.load();
-        while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
+    // Binned split (16 bins per axis): partitions ids and returns the size of the left part.
+    size_t splitBinned(uint32_t *ids, size_t n) {
         // the passes over a wide node are split over host threads: min / max and counts merge exactly, so the tree does
         // not depend on how many threads there are
         constexpr size_t kWide = 65536, kChunk = 16384;
@@ -619,6 +630,21 @@ struct SahBuilder {
             mid = (size_t)(m - ids);
             if (mid == 0 || mid == n) mid = n / 2;
         }
+        return mid;
+    }
+    Emitted build(uint32_t *ids, size_t n, uint32_t depth, uint32_t my) {
+        if (n == 1) return Emitted{pref[ids[0]], pbox[ids[0]]};
+        uint32_t seen = max_depth.load();
+        while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
+        if (n == 2) { // half of all nodes: nothing to bin
+            DevNode &d = (*nodes)[my];
+            const Box &a = pbox[ids[0]], &b = pbox[ids[1]];
+            d.set_box(0, a.mn, a.mx);
+            d.set_box(1, b.mn, b.mx);
+            d.left = pref[ids[0]]; d.right = pref[ids[1]]; d.pad0 = d.pad1 = 0;
+            return Emitted{my, boxUnion(a, b)};
+        }
+        const size_t mid = splitBinned(ids, n);
         Emitted l, r;
         // SAH splits are uneven (a ground sphere, a small mesh next to a big one), so the fan-out over host threads goes
         // by subtree size, not by depth; `spawned` bounds the number of threads ever created per build
