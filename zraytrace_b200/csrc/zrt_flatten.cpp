@@ -7,10 +7,13 @@
 //        (bvh.zig:193-204 accepts the right child only if strictly closer)            -> slot numbers
 //      * a node whose box has zero thickness on an axis is never entered, because
 //        aabb.zig:121 rejects on `tmax <= tmin`                            -> pruning
-// 2. Flatten what survives into 64-byte two-child nodes (DevNode) in DFS pre-order.
-// 3. By default (unless ZRT_FLAG_BVH_REFERENCE) throw the reference topology away and re-split the surviving
-//    primitives with a binned surface-area heuristic; slots keep the reference order, so the hits
-//    are the same and only the number of node fetches changes.
+//    Both are known where the build creates its leaves, so no pass over the finished tree is needed.  From 2048
+//    surfaces on the tree is built from presorted index lists without a sort inside the recursion (RefTree below).
+// 2. ZRT_FLAG_BVH_REFERENCE: flatten what survives into 64-byte two-child nodes (DevNode) in DFS pre-order.
+// 3. Default: throw the reference topology away and re-split the surviving primitives with a binned surface-area
+//    heuristic; slots keep the reference order, so the hits are the same and only the number of node fetches
+//    changes.
+// Measured phase by phase in DESIGN.md section 5.2 (ZRT_TIMING=1 prints them).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
