@@ -407,9 +407,15 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     // BVH scenes: the warp-scheduled state machine k_trace_ws is opt-in as well: with its best thresholds it ties with
     // k_trace on C2/C4 (13.6 vs 13.2 ms, 120 vs 122 ms) and loses on C3 (42.8 vs 37.2 ms), DESIGN.md section 4.1
     P.warp_scheduled = ((p->flags & ZRT_FLAG_KERNEL_WARP) && r->mode == MODE_BVH && !sorted) ? 1u : 0u;
-    P.ws_node_min = 8;   // keep stepping nodes while >= 8 lanes can
-    P.ws_leaf_min = 4;   // run postponed leaves once 4 lanes hold one
-    P.ws_shade_min = 24; // shade / regenerate once 24 lanes wait for it
+    // thresholds from tools/ws_sweep.py at 8 resident blocks per SM (profiles/r1_v10_ws_sweep.log): (12, 2, 20) runs C2 /
+    // C3 / C4 at 0.908 / 1.044 / 0.966 of the default kernel's time, the former (8, 4, 24) at 0.927 / 1.061 / 0.969
+    P.ws_node_min = 12;  // keep stepping nodes while >= 12 lanes can
+    P.ws_leaf_min = 2;   // run postponed leaves once 2 lanes hold one
+    P.ws_shade_min = 20; // shade / regenerate once 20 lanes wait for it
+    if (const char *e = std::getenv("ZRT_WS_THRESHOLDS")) { // "node,leaf,shade": tuning sweeps (tools/ws_sweep.sh)
+        unsigned a = 0, b = 0, c = 0;
+        if (std::sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { P.ws_node_min = a; P.ws_leaf_min = b; P.ws_shade_min = c; }
+    }
     P.halton = (p->flags & ZRT_FLAG_SAMPLER_HALTON) ? 1u : 0u;
     P.roulette = (p->flags & ZRT_FLAG_RUSSIAN_ROULETTE) ? 1u : 0u;
     if ((P.halton || P.roulette) && (p->flags & (ZRT_FLAG_KERNEL_SORTED | ZRT_FLAG_KERNEL_WARP)))
