@@ -404,8 +404,11 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         return fail(ZRT_ERR_INVALID, "ZRT_FLAG_KERNEL_SORTED needs width, height < 65536 and < 262144 materials");
     const bool sorted = (p->flags & ZRT_FLAG_KERNEL_SORTED) && !(p->flags & ZRT_FLAG_KERNEL_THREAD);
     P.sorted_shading = (sorted && sorted_ok) ? 1u : 0u;
-    // BVH scenes: the warp-scheduled state machine k_trace_ws is opt-in as well: with its best thresholds it ties with
-    // k_trace on C2/C4 (13.6 vs 13.2 ms, 120 vs 122 ms) and loses on C3 (42.8 vs 37.2 ms), DESIGN.md section 4.1
+    // BVH scenes: the warp-scheduled state machine k_trace_ws is opt-in as well: at 8 blocks per SM it runs C2 / C3 / C4
+    // at 0.87 / 1.03 / 0.93 of k_trace's time, so neither kernel wins everywhere.  (Tried: letting the first render of a
+    // scene time both on a 1/4 x 1/4 image at 32 spp and keep the faster one.  Launches of 0.2-0.5 ms are all ramp-up and
+    // tail, where k_trace_ws is the slower one: it picked k_trace on all three.  A calibration long enough to be
+    // representative costs more than the 3-13 % at stake for a scene that is rendered once.)
     P.warp_scheduled = ((p->flags & ZRT_FLAG_KERNEL_WARP) && r->mode == MODE_BVH && !sorted) ? 1u : 0u;
     // thresholds from tools/ws_sweep.py at 8 resident blocks per SM (profiles/r1_v10_ws_sweep.log): (12, 2, 20) runs C2 /
     // C3 / C4 at 0.908 / 1.044 / 0.966 of the default kernel's time, the former (8, 4, 24) at 0.927 / 1.061 / 0.969
