@@ -122,9 +122,11 @@ enum {
                                    (bvh.zig:62-185) instead of the binned-SAH tree libzrt builds by default over
                                    the same primitives; hits are identical either way (ties break on the
                                    reference DFS order, unreachable surfaces are pruned), only speed differs */
-    ZRT_FLAG_KERNEL_THREAD = 1u << 2, /* the one-thread-per-path megakernel k_trace (the default; wins over SORTED) */
-    ZRT_FLAG_KERNEL_WARP = 1u << 4,   /* BVH scenes: the warp-scheduled state machine k_trace_ws (opt-in, bit-identical
-                                   output; 13 % / 7 % faster than k_trace on configs 2 / 4, 3 % slower on config 3) */
+    ZRT_FLAG_KERNEL_THREAD = 1u << 2, /* force the one-thread-per-path megakernel k_trace (wins over SORTED) */
+    ZRT_FLAG_KERNEL_WARP = 1u << 4,   /* BVH scenes: the warp-scheduled state machine k_trace_ws (bit-identical
+                                   output; 13 % / 7 % faster than k_trace on configs 2 / 4, 3 % slower on config 3).
+                                   With neither flag a BVH launch of >= 2^24 samples runs k_trace_ws, a smaller one
+                                   k_trace; sphere-only and list scenes always run k_trace */
     ZRT_FLAG_RUSSIAN_ROULETTE = 1u << 5, /* src/README.md:5-6 TODO of the reference: from the 3rd ray of a path on,
                                    continue with probability p = clamp(max(throughput), 0.05, 1) and divide the
                                    throughput by p.  Changes the estimator's variance, not its expectation */

@@ -409,7 +409,11 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     // scene time both on a 1/4 x 1/4 image at 32 spp and keep the faster one.  Launches of 0.2-0.5 ms are all ramp-up and
     // tail, where k_trace_ws is the slower one: it picked k_trace on all three.  A calibration long enough to be
     // representative costs more than the 3-13 % at stake for a scene that is rendered once.)
-    P.warp_scheduled = ((p->flags & ZRT_FLAG_KERNEL_WARP) && r->mode == MODE_BVH && !sorted) ? 1u : 0u;
+    // What is affordable is a rule: launches large enough to be mostly steady state (>= 2^24 samples) take k_trace_ws
+    // unless a flag says otherwise, everything smaller k_trace.  On the three BVH configurations that is -13 %, +3 %, -7 %.
+    const bool ws_ok = r->mode == MODE_BVH && !sorted && !(p->flags & (ZRT_FLAG_SAMPLER_HALTON | ZRT_FLAG_RUSSIAN_ROULETTE));
+    const bool ws_auto = !(p->flags & (ZRT_FLAG_KERNEL_WARP | ZRT_FLAG_KERNEL_THREAD)) && pixels * plan->n_samples >= (1ull << 24);
+    P.warp_scheduled = (ws_ok && ((p->flags & ZRT_FLAG_KERNEL_WARP) || ws_auto)) ? 1u : 0u;
     // thresholds from tools/ws_sweep.py at 8 resident blocks per SM (profiles/r1_v10_ws_sweep.log): (12, 2, 20) runs C2 /
     // C3 / C4 at 0.908 / 1.044 / 0.966 of the default kernel's time, the former (8, 4, 24) at 0.927 / 1.061 / 0.969
     P.ws_node_min = 12;  // keep stepping nodes while >= 12 lanes can
