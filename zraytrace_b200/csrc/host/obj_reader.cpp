@@ -151,8 +151,8 @@ void parseChunk(Chunk &c) {
 
 template <class F>
 void forEachChunk(std::vector<Chunk> &chunks, F fn) {
-    std::vector<std::thread> th;
-    for (size_t i = 1; i < chunks.size(); i++) th.emplace_back([&, i] { fn(i); });
+    std::vector<zrt::Worker> th(chunks.size() - 1);
+    for (size_t i = 1; i < chunks.size(); i++) th[i - 1] = zrt::Worker([&, i] { fn(i); });
     fn(0);
     for (auto &t : th) t.join();
 }

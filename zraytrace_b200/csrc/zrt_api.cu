@@ -310,7 +310,14 @@ int selectRep(zrt_scene *sc, const zrt_params *p, DevRep **out) {
     DevRep *r = !use_bvh ? &sc->rep_list : ((p->flags & ZRT_FLAG_BVH_REFERENCE) ? &sc->rep_bvh : &sc->rep_sah);
     if (!r->ready) {
         const auto t0 = std::chrono::steady_clock::now();
-        const int rc = !use_bvh ? buildListRep(sc, *r) : buildBvhRep(sc, *r, r == &sc->rep_sah);
+        int rc;
+        try { // nothing may throw across the C ABI
+            rc = !use_bvh ? buildListRep(sc, *r) : buildBvhRep(sc, *r, r == &sc->rep_sah);
+        } catch (const std::bad_alloc &) {
+            return fail(ZRT_ERR_OOM, "out of host memory while flattening the scene");
+        } catch (const std::exception &e) {
+            return fail(ZRT_ERR_OOM, std::string("scene flattening failed: ") + e.what());
+        }
         if (rc != ZRT_OK) return rc;
         r->prepare_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
@@ -745,7 +752,12 @@ static const FlatBvh *hostBvh(zrt_scene *sc, uint32_t flags) {
     DevRep &r = k ? sc->rep_sah : sc->rep_bvh;
     if (r.ready) return &r.info;
     if (!sc->host_bvh_ready[k]) {
-        build_flat_bvh(sc->host, k != 0, &sc->host_bvh[k]);
+        try {
+            build_flat_bvh(sc->host, k != 0, &sc->host_bvh[k]);
+        } catch (const std::exception &e) {
+            fail(ZRT_ERR_OOM, std::string("scene flattening failed: ") + e.what());
+            return nullptr;
+        }
         sc->host_bvh_ready[k] = true;
     }
     return &sc->host_bvh[k];
@@ -756,6 +768,7 @@ uint64_t zrt_scene_launch_count(const zrt_scene *sc) { return sc ? sc->launch_co
 int zrt_scene_bvh_info(zrt_scene *sc, uint32_t flags, zrt_bvh_info *out) {
     if (!sc || !out) return fail(ZRT_ERR_INVALID, "NULL argument");
     const FlatBvh *b = hostBvh(sc, flags);
+    if (!b) return ZRT_ERR_OOM;
     out->nodes = (uint32_t)b->nodes.size();
     out->leaves = b->leaves;
     out->max_depth = b->max_depth;
@@ -768,6 +781,7 @@ int zrt_scene_bvh_info(zrt_scene *sc, uint32_t flags, zrt_bvh_info *out) {
 int zrt_scene_bvh_order(zrt_scene *sc, uint32_t *order, uint8_t *visible) {
     if (!sc || !order || !visible) return fail(ZRT_ERR_INVALID, "NULL argument");
     const FlatBvh *b = hostBvh(sc, 0);
+    if (!b) return ZRT_ERR_OOM;
     for (size_t s = 0; s < b->slot_surface.size(); s++) order[s] = b->slot_surface[s];
     std::memset(visible, 0, sc->host.surfaces.size());
     for (size_t s = 0; s < b->slot_surface.size(); s++) visible[b->slot_surface[s]] = b->slot_visible[s];

@@ -79,13 +79,13 @@ struct Raw {
 
 // f() on its own thread, or in line when a thread would cost more than the work
 struct Maybe {
-    std::thread t;
+    Worker w;
     template <class F>
     Maybe(bool threaded, F f) {
-        if (threaded) t = std::thread(f);
+        if (threaded) w = Worker(f);
         else f();
     }
-    void join() { if (t.joinable()) t.join(); }
+    void join() { w.join(); }
 };
 
 struct RefNode {          // one bvh.zig BVHNode
@@ -271,7 +271,7 @@ struct RefTree {
         const size_t split = optimalAxisDivide(ids, n);
         int32_t l, r;
         if (depth <= kParallelDepth && n >= kParallelMin) {
-            std::thread left([&] { l = divide(ids, split, depth + 1, base); });
+            Worker left([&] { l = divide(ids, split, depth + 1, base); });
             r = divide(ids + split, n - split, depth + 1, base + split);
             left.join();
         } else {
@@ -336,14 +336,14 @@ struct RefTree {
         for (size_t i = 0; i < at; i++) side[f[i]] = 0;
         for (size_t i = at; i < n; i++) side[f[i]] = 1;
         if (n >= kWideNode) { // four lists, four threads (the final order's own list doubles as the fourth scratch)
-            std::thread th[N_ORDERS];
+            Worker th[N_ORDERS];
             std::vector<uint32_t> extra[N_ORDERS];
             int used = 0;
             for (int k = 0; k < N_ORDERS; k++) {
                 if (k == final_order) continue;
                 uint32_t *tmp = part_tmp.data() + lo;
                 if (used++) { extra[k].resize(n); tmp = extra[k].data(); }
-                th[k] = std::thread([this, k, lo, n, tmp] { partitionList(k, lo, n, tmp); });
+                th[k] = Worker([this, k, lo, n, tmp] { partitionList(k, lo, n, tmp); });
             }
             for (int k = 0; k < N_ORDERS; k++) if (k != final_order) th[k].join();
             return;
@@ -355,8 +355,8 @@ struct RefTree {
         SplitSearch ss(n);
         Box seg[3][4];
         if (n >= kWideNode) {
-            std::thread ty([&] { segmentBoxes(ss, lists[1], n, seg[1]); });
-            std::thread tz([&] { segmentBoxes(ss, lists[2], n, seg[2]); });
+            Worker ty([&] { segmentBoxes(ss, lists[1], n, seg[1]); });
+            Worker tz([&] { segmentBoxes(ss, lists[2], n, seg[2]); });
             segmentBoxes(ss, lists[0], n, seg[0]);
             ty.join();
             tz.join();
@@ -373,7 +373,7 @@ struct RefTree {
         partitionLists(lo, n, final_order, at);
         int32_t l, r;
         if (std::min(at, n - at) >= kParallelMin && spawned.fetch_add(1) < 64) {
-            std::thread left([&] { l = dividePresorted(lo, at, final_order, child_x, depth + 1); });
+            Worker left([&] { l = dividePresorted(lo, at, final_order, child_x, depth + 1); });
             r = dividePresorted(lo + at, n - at, final_order, child_x, depth + 1);
             left.join();
         } else {
@@ -653,7 +653,7 @@ struct SahBuilder {
         // by subtree size, not by depth; `spawned` bounds the number of threads ever created per build
         const size_t small = std::min(mid, n - mid);
         if (small >= RefTree::kParallelMin && spawned.fetch_add(1) < 64) {
-            std::thread left([&] { l = build(ids, mid, depth + 1, my + 1); });
+            Worker left([&] { l = build(ids, mid, depth + 1, my + 1); });
             r = build(ids + mid, n - mid, depth + 1, my + (uint32_t)mid);
             left.join();
         } else {

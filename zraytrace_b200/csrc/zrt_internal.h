@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -146,6 +147,23 @@ struct KParams {
 
 enum TraceMode { MODE_SPHERES = 0, MODE_LIST = 1, MODE_BVH = 2 };
 
+// A helper thread that cannot fail: if the system refuses another thread, the work runs on the caller's.
+struct Worker {
+    std::thread t;
+    Worker() = default;
+    template <class F>
+    explicit Worker(F f) {
+        try {
+            t = std::thread(f);
+        } catch (const std::system_error &) {
+            f();
+        }
+    }
+    void join() {
+        if (t.joinable()) t.join();
+    }
+};
+
 // fn(begin, end) over [0, n) in contiguous chunks on up to 16 host threads
 template <class F>
 void parallelFor(size_t n, size_t min_chunk, F fn) {
@@ -153,9 +171,9 @@ void parallelFor(size_t n, size_t min_chunk, F fn) {
     static const size_t hw = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
     const size_t threads = std::min(hw, n / min_chunk);
     if (threads <= 1) { fn((size_t)0, n); return; }
-    std::vector<std::thread> th;
+    std::vector<Worker> th(threads - 1);
     const size_t chunk = (n + threads - 1) / threads;
-    for (size_t t = 1; t < threads; t++) th.emplace_back([=] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+    for (size_t t = 1; t < threads; t++) th[t - 1] = Worker([=] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
     fn((size_t)0, std::min(n, chunk));
     for (auto &t : th) t.join();
 }
