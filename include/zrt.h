@@ -135,6 +135,9 @@ enum {
                                    independent uniforms.  Both extensions run on k_trace only and are restated by
                                    the oracle (draw-for-draw parity); zrt_trace_statistics ignores them */
     ZRT_FLAG_KERNEL_X2 = 1u << 7,     /* spheres-only scenes: k_trace_x2, two paths per thread in packed f32x2 (opt-in: ties) */
+    ZRT_FLAG_KERNEL_POOL = 1u << 8,   /* spheres-only scenes: k_trace_pool, every warp keeps a pool of work items in shared
+                                   memory and runs batches of up to 32 paths that need the same thing next (new sample,
+                                   Lambertian, metal, glass); bit-identical output.  Ignored on other scenes */
     ZRT_FLAG_KERNEL_SORTED = 1u << 3  /* the block-sorted-shading kernel k_trace_sorted (shared-memory wavefront
                                    inside a thread block).  Images and counters are bit-identical between the
                                    two kernels, only speed differs; the thread kernel measured faster */
@@ -201,6 +204,10 @@ int zrt_render_rgb8(zrt_scene *scene, const zrt_camera *camera, const zrt_params
  * that the accumulators can be summed with one NCCL reduce without touching the host. */
 int zrt_render_device(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
                       float *d_rgb, uint64_t *d_counters, void *stream);
+
+/* Optional pieces compiled into this build of the library. */
+enum { ZRT_FEATURE_EXPERIMENTS = 1u << 0 /* k_trace_sorted / k_trace_x2 (make EXPERIMENTS=1); without it their flags fail */ };
+uint32_t zrt_build_features(void);
 
 /* Number of libzrt kernels launched on behalf of this scene since it was created (trace, resolve and
  * primary-hit kernels; driver memsets and copies are not counted). */

@@ -812,18 +812,16 @@ int zro_render(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_p
     return ZRT_OK;
 }
 
-int zro_primary_hits(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_params *p, int jitter,
-                     int traversal_mode, uint32_t *surface_id, float *t_out) {
-    if (!validate(desc) || !camera || !p || !surface_id || !t_out) return ZRT_ERR_INVALID;
-    Scene sc;
-    buildScene(sc, desc, p->bounded_volume_hierarchy != 0);
+// rows [y0, y1) of the first-hit AOV; each row only reads the scene, so rows can run on separate threads
+static void primaryRows(const Scene &sc, const zrt_camera *camera, const zrt_params *p, int jitter, int traversal_mode,
+                        uint32_t y0, uint32_t y1, uint32_t y_step, uint32_t *surface_id, float *t_out) {
     Stats stats;
     Ctx cx{traversal_mode, &stats};
     const f32 f_width = (f32)p->width, f_height = (f32)p->height;
     Rng rng{ZRO_RNG_CTR, nullptr};
     rng.seed32 = foldSeed(p->seed);
     rng.sample = p->sample_begin;
-    for (uint32_t y = 0; y < p->height; y++)
+    for (uint32_t y = y0; y < y1; y += y_step)
         for (uint32_t x = 0; x < p->width; x++) {
             f32 xi_u = 0.0f, xi_v = 0.0f;
             rng.pixel = y * p->width + x;
@@ -841,7 +839,27 @@ int zro_primary_hits(const zrt_scene_desc *desc, const zrt_camera *camera, const
                 t_out[o] = std::numeric_limits<f32>::infinity();
             }
         }
+}
+
+int zro_primary_hits_mt(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_params *p, int jitter,
+                        int traversal_mode, int n_threads, uint32_t *surface_id, float *t_out) {
+    if (!validate(desc) || !camera || !p || !surface_id || !t_out) return ZRT_ERR_INVALID;
+    Scene sc;
+    buildScene(sc, desc, p->bounded_volume_hierarchy != 0);
+    if (n_threads <= 1) {
+        primaryRows(sc, camera, p, jitter, traversal_mode, 0, p->height, 1, surface_id, t_out);
+        return ZRT_OK;
+    }
+    std::vector<std::thread> th; // interleaved scanlines, as zro_render
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&, t]() { primaryRows(sc, camera, p, jitter, traversal_mode, (uint32_t)t, p->height, (uint32_t)n_threads, surface_id, t_out); });
+    for (auto &t : th) t.join();
     return ZRT_OK;
+}
+
+int zro_primary_hits(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_params *p, int jitter,
+                     int traversal_mode, uint32_t *surface_id, float *t_out) {
+    return zro_primary_hits_mt(desc, camera, p, jitter, traversal_mode, 1, surface_id, t_out);
 }
 
 static void dfsOrder(const Surface *s, bool under_flat, std::vector<uint32_t> &order, std::vector<uint8_t> &vis,

@@ -62,6 +62,10 @@ int zro_render(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_p
 int zro_primary_hits(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_params *params,
                      int jitter, int traversal_mode, uint32_t *surface_id, float *t);
 
+/* the same rows on n_threads host threads (scanline-interleaved; every pixel is independent, results identical) */
+int zro_primary_hits_mt(const zrt_scene_desc *desc, const zrt_camera *camera, const zrt_params *params,
+                        int jitter, int traversal_mode, int n_threads, uint32_t *surface_id, float *t);
+
 /* DFS (left-first) order of the surfaces in the reference tree and which of them can never be hit
  * because they sit under a zero-thickness box (Q4).  order/visible have n_surfaces entries. */
 int zro_bvh_order(const zrt_scene_desc *desc, uint32_t *order, uint8_t *visible, zro_stats *stats);

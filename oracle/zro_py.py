@@ -44,6 +44,8 @@ def lib():
                                  C.c_int, C.c_int, C.c_void_p, C.POINTER(A.Counters), C.POINTER(Stats)]
         L.zro_primary_hits.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(A.Camera), C.POINTER(A.Params), C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p]
+        L.zro_primary_hits_mt.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(A.Camera), C.POINTER(A.Params), C.c_int,
+                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.zro_bvh_order.argtypes = [C.POINTER(A.SceneDesc), C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         L.zro_camera_init.argtypes = [f3, f3, f3, C.c_float, C.c_float, C.POINTER(A.Camera)]
         L.zro_vec3_dot.restype = C.c_float
@@ -81,11 +83,14 @@ def render(scene, camera, params, rng=RNG_CTR, traversal=TRAVERSAL_REF, math=MAT
     return img, cnt, st
 
 
-def primary_hits(scene, camera, params, jitter=0, traversal=TRAVERSAL_REF):
+def primary_hits(scene, camera, params, jitter=0, traversal=TRAVERSAL_REF, threads=1):
+    """First rayColor iteration per pixel through the oracle's pointer tree.  threads > 1 only spreads the rows
+    over host cores (pixels are independent); TRAVERSAL_TIGHT visits ~50x fewer nodes than the literal aabb.zig
+    test and returns the same hits."""
     ids = np.zeros((params.height, params.width), np.uint32)
     t = np.zeros((params.height, params.width), np.float32)
-    rc = lib().zro_primary_hits(C.byref(scene.desc), C.byref(camera), C.byref(params), jitter, traversal,
-                                ids.ctypes.data, t.ctypes.data)
+    rc = lib().zro_primary_hits_mt(C.byref(scene.desc), C.byref(camera), C.byref(params), jitter, traversal, threads,
+                                   ids.ctypes.data, t.ctypes.data)
     if rc != 0:
         raise RuntimeError(f"zro_primary_hits failed: {rc}")
     return ids, t

@@ -196,3 +196,25 @@ def test_showcase_image_7spheres():
 
     rmse = np.sqrt(((pool(q) - pool(gold)) ** 2).mean(axis=(0, 1)))
     assert (rmse < 0.02).all(), rmse
+
+
+@pytest.mark.parametrize("name", ["teapot", "bunny_glass", "man"])
+def test_tight_traversal_returns_the_hits_of_the_literal_aabb_test(name):
+    """aabb.zig:109-127 does not carry the interval between axes; the oracle's interval-carrying test on
+    the same pointer tree must be result-neutral: same first hits bit for bit, same full-depth paths (every counter
+    and every pixel), only the visit counts differ.  The GPU tests at BASELINE sizes lean on this."""
+    from tests import scenes_py
+    from zraytrace_b200 import _abi as A
+    sc, cam = {"teapot": scenes_py.teapot_and_ball, "man": scenes_py.man_and_ball,
+               "bunny_glass": lambda: scenes_py.bunny_and_ball(dielectric=True)}[name]()
+    p = A.make_params(48, 48, 2, 30)
+    ids_r, t_r = zro_py.primary_hits(sc, cam, p, traversal=zro_py.TRAVERSAL_REF, threads=2)
+    ids_t, t_t = zro_py.primary_hits(sc, cam, p, traversal=zro_py.TRAVERSAL_TIGHT)
+    assert np.array_equal(ids_r, ids_t) and np.array_equal(t_r.view(np.uint32), t_t.view(np.uint32))
+    assert (ids_r != A.ZRT_NO_HIT).mean() > 0.2
+    p = A.make_params(24, 24, 2, 30)
+    for rng, math in ((zro_py.RNG_CTR, zro_py.MATH_SPEC), (zro_py.RNG_REF, zro_py.MATH_LIBM)):
+        img_r, c_r, st_r = zro_py.render(sc, cam, p, rng=rng, math=math, traversal=zro_py.TRAVERSAL_REF)
+        img_t, c_t, st_t = zro_py.render(sc, cam, p, rng=rng, math=math, traversal=zro_py.TRAVERSAL_TIGHT)
+        assert c_r.as_dict() == c_t.as_dict() and np.array_equal(img_r.view(np.uint32), img_t.view(np.uint32))
+        assert st_t.box_tests * 5 < st_r.box_tests  # the literal test barely culls

@@ -102,4 +102,4 @@ def test_device_matches_oracle_draw_for_draw(name, w, spp, depth, flags):
         assert tot == c_g.as_dict()
         np.testing.assert_allclose(acc * np.float32(1.0 / spp), img_g, rtol=1e-5, atol=1e-6)
         with pytest.raises(Z.ZrtError):
-            dev.render(cam, A.make_params(w, w, spp, depth, flags=flags | A.ZRT_FLAG_KERNEL_SORTED))
+            dev.render(cam, A.make_params(w, w, spp, depth, flags=flags | A.ZRT_FLAG_KERNEL_WARP))

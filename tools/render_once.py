@@ -19,7 +19,7 @@ ap.add_argument("--reftree", action="store_true")
 ap.add_argument("--chunks", type=int, default=0)
 ap.add_argument("--primary", action="store_true")
 ap.add_argument("--size", type=int, default=0, help="override width = height")
-ap.add_argument("--kernel", default="auto", choices=["auto", "thread", "sorted", "warp", "x2"])
+ap.add_argument("--kernel", default="auto", choices=["auto", "thread", "sorted", "warp", "x2", "pool"])
 a = ap.parse_args()
 wl = dict(bench.WORKLOADS[a.workload])
 if a.spp:
@@ -27,7 +27,7 @@ if a.spp:
 if a.size:
     wl["w"] = wl["h"] = a.size
 hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0))
-kflag = {"auto": 0, "thread": A.ZRT_FLAG_KERNEL_THREAD, "sorted": A.ZRT_FLAG_KERNEL_SORTED, "warp": A.ZRT_FLAG_KERNEL_WARP, "x2": A.ZRT_FLAG_KERNEL_X2}[a.kernel]
+kflag = {"auto": 0, "thread": A.ZRT_FLAG_KERNEL_THREAD, "sorted": A.ZRT_FLAG_KERNEL_SORTED, "warp": A.ZRT_FLAG_KERNEL_WARP, "x2": A.ZRT_FLAG_KERNEL_X2, "pool": A.ZRT_FLAG_KERNEL_POOL}[a.kernel]
 p = bench.params_for(wl, flags=(A.ZRT_FLAG_BVH_REFERENCE if a.reftree else 0) | kflag, sample_chunks=a.chunks)
 with Z.Scene(hs, device=0) as sc:
     for i in range(a.reps):

@@ -7,8 +7,9 @@ ZRT_MATERIAL_LAMBERTIAN, ZRT_MATERIAL_METAL, ZRT_MATERIAL_DIELECTRIC = 0, 1, 2
 ZRT_TEXTURE_COLOR, ZRT_TEXTURE_IMAGE = 0, 1
 ZRT_XLIMIT_HEIGHT, ZRT_XLIMIT_WIDTH = 0, 1
 ZRT_FLAG_RAW_SUM, ZRT_FLAG_BVH_REFERENCE, ZRT_FLAG_KERNEL_THREAD, ZRT_FLAG_KERNEL_SORTED, ZRT_FLAG_KERNEL_WARP = 1, 2, 4, 8, 16
-ZRT_FLAG_RUSSIAN_ROULETTE, ZRT_FLAG_SAMPLER_HALTON, ZRT_FLAG_KERNEL_X2 = 32, 64, 128
+ZRT_FLAG_RUSSIAN_ROULETTE, ZRT_FLAG_SAMPLER_HALTON, ZRT_FLAG_KERNEL_X2, ZRT_FLAG_KERNEL_POOL = 32, 64, 128, 256
 ZRT_NO_HIT = 0xFFFFFFFF
+ZRT_FEATURE_EXPERIMENTS = 1
 
 
 class Vec3(C.Structure):

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <vector>
 
 #include "../../../include/zrt_host.h"
@@ -42,8 +43,20 @@ void writeChunk(std::vector<uint8_t> &png, const char type[4], const std::vector
 
 } // namespace
 
+static int pngRead(const char *path, uint8_t **pixels, uint32_t *width, uint32_t *height, uint32_t *channels);
+
 extern "C" int zrt_host_png_read(const char *path, uint8_t **pixels, uint32_t *width, uint32_t *height, uint32_t *channels) {
     if (!path || !pixels || !width || !height || !channels) return ZRT_ERR_INVALID;
+    try { // nothing throws across the C ABI (an IHDR can ask for more memory than there is)
+        return pngRead(path, pixels, width, height, channels);
+    } catch (const std::bad_alloc &) {
+        return ZRT_ERR_OOM;
+    } catch (...) {
+        return ZRT_ERR_IO;
+    }
+}
+
+static int pngRead(const char *path, uint8_t **pixels, uint32_t *width, uint32_t *height, uint32_t *channels) {
     std::vector<uint8_t> file;
     if (!readAll(path, &file)) return ZRT_ERR_IO;
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
@@ -72,6 +85,7 @@ extern "C" int zrt_host_png_read(const char *path, uint8_t **pixels, uint32_t *w
         pos += 12 + len;
     }
     if (w == 0 || h == 0 || ch == 0) return ZRT_ERR_IO;
+    if ((uint64_t)w * h > (1ull << 28)) return ZRT_ERR_INVALID; // an untrusted header does not get to size the allocation
     const size_t stride = (size_t)w * ch;
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf raw_len = (uLongf)raw.size();
@@ -106,6 +120,7 @@ static int writePngRaw(const char *path, const std::vector<uint8_t> &raw, uint32
 
 extern "C" int zrt_host_png_write(const char *path, const float *rgb, uint32_t width, uint32_t height) {
     if (!path || !rgb || width == 0 || height == 0) return ZRT_ERR_INVALID;
+    try {
     const size_t stride = (size_t)width * 3;
     std::vector<uint8_t> raw((stride + 1) * height);
     for (uint32_t y = 0; y < height; y++) {
@@ -120,10 +135,14 @@ extern "C" int zrt_host_png_write(const char *path, const float *rgb, uint32_t w
         }
     }
     return writePngRaw(path, raw, width, height);
+    } catch (const std::bad_alloc &) {
+        return ZRT_ERR_OOM;
+    }
 }
 
 extern "C" int zrt_host_png_write_rgb8(const char *path, const uint8_t *rgb8, uint32_t width, uint32_t height) {
     if (!path || !rgb8 || width == 0 || height == 0) return ZRT_ERR_INVALID;
+    try {
     const size_t stride = (size_t)width * 3;
     std::vector<uint8_t> raw((stride + 1) * height);
     for (uint32_t y = 0; y < height; y++) {
@@ -131,6 +150,9 @@ extern "C" int zrt_host_png_write_rgb8(const char *path, const uint8_t *rgb8, ui
         std::memcpy(&raw[(stride + 1) * y + 1], rgb8 + stride * y, stride);
     }
     return writePngRaw(path, raw, width, height);
+    } catch (const std::bad_alloc &) {
+        return ZRT_ERR_OOM;
+    }
 }
 
 static int writePngRaw(const char *path, const std::vector<uint8_t> &raw, uint32_t width, uint32_t height) {

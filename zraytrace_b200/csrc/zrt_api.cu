@@ -65,11 +65,14 @@ template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
-    cudaError_t upload(const std::vector<T> &v) { return upload(v.data(), v.size()); }
-    cudaError_t upload(const T *src, size_t count) {
+    // H2D on `st`: ordered before everything enqueued on `st` afterwards.  For pageable memory the call returns once
+    // the source has been staged, so the caller may free `src` right away; the scene builders synchronise `st` once
+    // at the end, which makes the data visible to every other stream as well.
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t st) { return upload(v.data(), v.size(), st); }
+    cudaError_t upload(const T *src, size_t count, cudaStream_t st) {
         cudaError_t e = reserve(count);
         if (e != cudaSuccess || count == 0) return e;
-        return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st);
     }
     cudaError_t reserve(size_t count) {
         if (count <= n) return cudaSuccess;
@@ -134,6 +137,11 @@ struct zrt_scene {
     uint64_t launch_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // zrt_render_device enqueues on the CALLER's stream while the scene's buffers are freed on the allocation stream:
+    // ev_user marks the end of the last such render, and everything that frees, grows or reuses a scene buffer waits
+    // for it first (quiesce / orderAfterUser).  A scene is used from one stream at a time.
+    cudaEvent_t ev_user = nullptr;
+    bool user_pending = false;
 };
 
 namespace {
@@ -190,6 +198,14 @@ int validate(const zrt_scene_desc *d) {
             return fail(ZRT_ERR_INVALID, "unknown surface kind");
         }
     }
+    // non-finite coordinates break the strict weak ordering of the BVH builder's sorts (undefined behaviour)
+    auto finite3 = [](const zrt_vec3 &v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); };
+    for (uint32_t i = 0; i < d->n_spheres; i++)
+        if (!finite3(d->spheres[i].center) || !std::isfinite(d->spheres[i].radius))
+            return fail(ZRT_ERR_INVALID, "sphere with a non-finite centre or radius");
+    for (uint32_t i = 0; i < d->n_triangles; i++)
+        if (!finite3(d->triangles[i].a) || !finite3(d->triangles[i].b) || !finite3(d->triangles[i].c))
+            return fail(ZRT_ERR_INVALID, "triangle with a non-finite vertex");
     for (uint32_t i = 0; i < d->n_materials; i++) {
         const zrt_material &m = d->materials[i];
         if (m.kind > ZRT_MATERIAL_DIELECTRIC) return fail(ZRT_ERR_INVALID, "unknown material kind");
@@ -215,7 +231,7 @@ int uploadMaterials(zrt_scene *sc) {
         const zrt_texture &t = hs.textures[i];
         if (t.kind != ZRT_TEXTURE_IMAGE) continue;
         // straight from the caller's pixels (page-locked or not): a device scene keeps no host copy of the texels
-        CUDA_TRY(sc->d_texels[i].upload(t.pixels, (size_t)t.width * t.height * t.channels));
+        CUDA_TRY(sc->d_texels[i].upload(t.pixels, (size_t)t.width * t.height * t.channels, sc->stream));
     }
     for (size_t i = 0; i < mats.size(); i++) {
         const zrt_material &m = hs.materials[i];
@@ -235,7 +251,8 @@ int uploadMaterials(zrt_scene *sc) {
         }
         mats[i] = d;
     }
-    CUDA_TRY(sc->mats.upload(mats));
+    CUDA_TRY(sc->mats.upload(mats, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream)); // visible to any stream a later zrt_render_device is given
     return ZRT_OK;
 }
 
@@ -258,12 +275,14 @@ int buildListRep(zrt_scene *sc, DevRep &r) {
     r.n_spheres = (uint32_t)r.h_spheres.size();
     r.n_list = n;
     r.mode = (sc->all_spheres && n <= MAX_INLINE_SPHERES && n > 0) ? MODE_SPHERES : MODE_LIST;
-    CUDA_TRY(r.spheres.upload(r.h_spheres));
-    CUDA_TRY(r.list.upload(list));
+    cudaStream_t st = sc->stream;
+    CUDA_TRY(r.spheres.upload(r.h_spheres, st));
+    CUDA_TRY(r.list.upload(list, st));
     if (hs.triangles.size()) {
-        CUDA_TRY(r.triA.upload(A)); CUDA_TRY(r.triE1.upload(E1)); CUDA_TRY(r.triE2.upload(E2));
-        CUDA_TRY(r.triMeta.upload(meta));
+        CUDA_TRY(r.triA.upload(A, st)); CUDA_TRY(r.triE1.upload(E1, st)); CUDA_TRY(r.triE2.upload(E2, st));
+        CUDA_TRY(r.triMeta.upload(meta, st));
     }
+    CUDA_TRY(cudaStreamSynchronize(st));
     r.ready = true;
     return ZRT_OK;
 }
@@ -295,10 +314,12 @@ int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
     r.n_list = 0;
     r.root = r.info.root;
     r.mode = MODE_BVH;
-    CUDA_TRY(r.spheres.upload(r.h_spheres));
-    CUDA_TRY(r.triA.upload(A)); CUDA_TRY(r.triE1.upload(E1)); CUDA_TRY(r.triE2.upload(E2));
-    CUDA_TRY(r.triMeta.upload(meta));
-    CUDA_TRY(r.nodes.upload(r.info.nodes.data(), r.info.nodes.size()));
+    cudaStream_t st = sc->stream;
+    CUDA_TRY(r.spheres.upload(r.h_spheres, st));
+    CUDA_TRY(r.triA.upload(A, st)); CUDA_TRY(r.triE1.upload(E1, st)); CUDA_TRY(r.triE2.upload(E2, st));
+    CUDA_TRY(r.triMeta.upload(meta, st));
+    CUDA_TRY(r.nodes.upload(r.info.nodes.data(), r.info.nodes.size(), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     lap("upload");
     r.ready = true;
     return ZRT_OK;
@@ -383,7 +404,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.lanes = lanes;
     P.lanes_log2 = 0;
     while ((1u << P.lanes_log2) < lanes) P.lanes_log2++;
-    P.x_end_magic = P.x_end > 1 ? (uint32_t)((0x100000000ull + P.x_end - 1) / P.x_end) : 0u;
+    P.x_end_magic = P.x_end > 1 ? (uint32_t)((0x100000000ull + P.x_end - 1) / P.x_end) : 0xFFFFFFFFu; // see item_decode
     P.max_depth = p->max_depth;
     P.seed32 = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
     P.color_scale = (p->flags & ZRT_FLAG_RAW_SUM) ? 1.0f : 1.0f / (float)p->samples_per_pixel; // raytrace.zig:157
@@ -406,6 +427,10 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     // kernel choice: the one-thread-per-path megakernel measured faster on every workload (C5: 43.2 ms against
     // 55.9 ms, DESIGN.md "Megakernel vs wavefront"), so block-sorted shading is opt-in.  It packs (px, py) into
     // 16 bits each and the material index into 18 bits.
+#ifndef ZRT_EXPERIMENTS
+    if (p->flags & (ZRT_FLAG_KERNEL_SORTED | ZRT_FLAG_KERNEL_X2))
+        return fail(ZRT_ERR_INVALID, "ZRT_FLAG_KERNEL_SORTED / ZRT_FLAG_KERNEL_X2 are experiments: build libzrt with EXPERIMENTS=1");
+#endif
     const bool sorted_ok = p->width < 65536u && p->height < 65536u && sc->host.materials.size() < (1u << 18);
     if ((p->flags & ZRT_FLAG_KERNEL_SORTED) && !sorted_ok)
         return fail(ZRT_ERR_INVALID, "ZRT_FLAG_KERNEL_SORTED needs width, height < 65536 and < 262144 materials");
@@ -445,16 +470,41 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
             e.ncx[0] = e.ncx[1] = -sp.cx; e.ncy[0] = e.ncy[1] = -sp.cy; e.ncz[0] = e.ncz[1] = -sp.cz;
             e.nr2[0] = e.nr2[1] = -sp.r2;
         }
-    P.two_paths = (r->mode == MODE_SPHERES && (p->flags & ZRT_FLAG_KERNEL_X2) && !P.sorted_shading && !P.halton && !P.roulette) ? 1u : 0u;
+    // k_trace_pool (K1q): spheres-only scenes, bounce count and pixel coordinates packed in 16 bits each
+    P.inl_kinds = 0;
+    if (r->mode == MODE_SPHERES)
+        for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++)
+            P.inl_kinds |= ((r->h_spheres[i].material >> MAT_KIND_SHIFT) & 3u) << (2u * i);
+    const bool pool_ok = r->mode == MODE_SPHERES && p->max_depth < 65535u && p->width < 65536u && p->height < 65536u &&
+                         !P.halton && !P.roulette && !P.sorted_shading;
+    if ((p->flags & ZRT_FLAG_KERNEL_POOL) && !(p->flags & ZRT_FLAG_KERNEL_THREAD) && pool_ok) {
+        P.pool = 64;
+        if (const char *e = std::getenv("ZRT_POOL_SLOTS")) P.pool = (uint32_t)std::atoi(e) >= 128u ? 128u : 64u;
+    }
+    P.two_paths = (r->mode == MODE_SPHERES && (p->flags & ZRT_FLAG_KERNEL_X2) && !P.sorted_shading && !P.halton && !P.roulette && !P.pool) ? 1u : 0u;
     plan->mode = r->mode;
     plan->n_floats = (size_t)p->width * p->height * 3;
     return ZRT_OK;
+}
+
+// the host waits until the last render enqueued on a caller's stream has finished (before scene buffers are freed or
+// reallocated: cudaFreeAsync on the allocation stream is not ordered after the caller's stream)
+void quiesce(zrt_scene *sc) {
+    if (sc->user_pending && sc->ev_user) cudaEventSynchronize(sc->ev_user);
+    sc->user_pending = false;
+}
+// `st` waits for the last render on a caller's stream: two renders of one scene share its scratch buffers
+cudaError_t orderAfterUser(zrt_scene *sc, cudaStream_t st) {
+    if (!sc->user_pending) return cudaSuccess;
+    return cudaStreamWaitEvent(st, sc->ev_user, 0);
 }
 
 // enqueue everything for one render on `st`; d_rgb receives the final image
 int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d_counters, cudaStream_t st,
                   cudaEvent_t e_k0, cudaEvent_t e_k1, cudaEvent_t e_r1, uint32_t *launches, uint8_t *d_rgb8 = nullptr) {
     KParams &P = plan.P;
+    if ((P.lanes > 1 && plan.n_floats * P.lanes > sc->part.n) || sc->work.n < 1) quiesce(sc); // about to reallocate scratch
+    CUDA_TRY(orderAfterUser(sc, st));
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 6 * sizeof(unsigned long long), st));
     float *trace_out = d_rgb;
     if (P.lanes > 1) {
@@ -558,6 +608,7 @@ int zrt_scene_create(const zrt_scene_desc *desc, int device, zrt_scene **out) {
         cudaError_t e = cudaSetDevice(device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking);
         for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&sc->ev[i]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sc->ev_user, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             const std::string msg = cudaGetErrorString(e);
             zrt_scene_destroy(sc);
@@ -591,6 +642,7 @@ void zrt_scene_destroy(zrt_scene *sc) {
     if (!sc) return;
     if (sc->device >= 0) {
         cudaSetDevice(sc->device);
+        quiesce(sc); // renders enqueued on a caller's stream may still be reading the buffers freed below
         if (sc->stream) cudaStreamSynchronize(sc->stream);
         sc->rep_list.release(); sc->rep_bvh.release(); sc->rep_sah.release();
         sc->mats.release(); sc->part.release(); sc->image.release(); sc->image8.release(); sc->counters.release();
@@ -598,17 +650,20 @@ void zrt_scene_destroy(zrt_scene *sc) {
         for (auto &t : sc->d_texels) t.release();
         for (auto &e : sc->ev)
             if (e) cudaEventDestroy(e);
+        if (sc->ev_user) cudaEventDestroy(sc->ev_user);
         if (sc->stream) cudaStreamDestroy(sc->stream);
     }
     delete sc;
 }
 
-int zrt_render(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, float *out_rgb,
-               zrt_counters *counters, zrt_timing *timing) {
+// raytrace.render() with host buffers out: the float image (out_rgb) or the 8-bit image of the fused output stage (out_rgb8)
+static int renderToHost(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, float *out_rgb, uint8_t *out_rgb8,
+                        zrt_counters *counters, zrt_timing *timing) {
     int rc = requireDevice(sc);
     if (rc != ZRT_OK) return rc;
-    if (!out_rgb) return fail(ZRT_ERR_INVALID, "out_rgb is NULL");
+    if (!out_rgb && !out_rgb8) return fail(ZRT_ERR_INVALID, out_rgb8 ? "out_rgb8 is NULL" : "out_rgb is NULL");
     if (!params) return fail(ZRT_ERR_INVALID, "params is NULL");
+    if (out_rgb8 && (params->flags & ZRT_FLAG_RAW_SUM)) return fail(ZRT_ERR_INVALID, "ZRT_FLAG_RAW_SUM has no 8-bit form");
     DevRep *rep = nullptr;
     const auto t_prep0 = std::chrono::steady_clock::now();
     rc = selectRep(sc, params, &rep);
@@ -617,12 +672,16 @@ int zrt_render(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params
     Plan plan;
     rc = makePlan(sc, camera, params, rep, &plan);
     if (rc != ZRT_OK) return rc;
+    if (plan.n_floats > sc->image.n || (out_rgb8 && plan.n_floats > sc->image8.n)) quiesce(sc);
     CUDA_TRY(sc->image.reserve(plan.n_floats));
-    CUDA_TRY(sc->counters.reserve(6));
+    if (out_rgb8) CUDA_TRY(sc->image8.reserve(plan.n_floats));
+    CUDA_TRY(sc->counters.reserve(10));
     uint32_t launches = 0;
-    rc = enqueueRender(sc, plan, sc->image.p, sc->counters.p, sc->stream, sc->ev[0], sc->ev[1], sc->ev[2], &launches);
+    rc = enqueueRender(sc, plan, sc->image.p, sc->counters.p, sc->stream, sc->ev[0], sc->ev[1], sc->ev[2], &launches,
+                       out_rgb8 ? sc->image8.p : nullptr);
     if (rc != ZRT_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_rgb, sc->image.p, plan.n_floats * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    if (out_rgb8) CUDA_TRY(cudaMemcpyAsync(out_rgb8, sc->image8.p, plan.n_floats, cudaMemcpyDeviceToHost, sc->stream));
+    else CUDA_TRY(cudaMemcpyAsync(out_rgb, sc->image.p, plan.n_floats * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
     unsigned long long h_counters[6];
     CUDA_TRY(cudaMemcpyAsync(h_counters, sc->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, sc->stream));
     CUDA_TRY(cudaEventRecord(sc->ev[3], sc->stream));
@@ -650,54 +709,16 @@ int zrt_render(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params
     return ZRT_OK;
 }
 
+int zrt_render(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, float *out_rgb,
+               zrt_counters *counters, zrt_timing *timing) {
+    if (!out_rgb) return fail(ZRT_ERR_INVALID, "out_rgb is NULL");
+    return renderToHost(sc, camera, params, out_rgb, nullptr, counters, timing);
+}
+
 int zrt_render_rgb8(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, uint8_t *out_rgb8,
                     zrt_counters *counters, zrt_timing *timing) {
-    int rc = requireDevice(sc);
-    if (rc != ZRT_OK) return rc;
     if (!out_rgb8) return fail(ZRT_ERR_INVALID, "out_rgb8 is NULL");
-    if (!params) return fail(ZRT_ERR_INVALID, "params is NULL");
-    if (params->flags & ZRT_FLAG_RAW_SUM) return fail(ZRT_ERR_INVALID, "ZRT_FLAG_RAW_SUM has no 8-bit form");
-    DevRep *rep = nullptr;
-    const auto t_prep0 = std::chrono::steady_clock::now();
-    rc = selectRep(sc, params, &rep);
-    if (rc != ZRT_OK) return rc;
-    const float prep_now = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_prep0).count();
-    Plan plan;
-    rc = makePlan(sc, camera, params, rep, &plan);
-    if (rc != ZRT_OK) return rc;
-    CUDA_TRY(sc->image.reserve(plan.n_floats));
-    CUDA_TRY(sc->image8.reserve(plan.n_floats));
-    CUDA_TRY(sc->counters.reserve(10));
-    uint32_t launches = 0;
-    rc = enqueueRender(sc, plan, sc->image.p, sc->counters.p, sc->stream, sc->ev[0], sc->ev[1], sc->ev[2], &launches,
-                       sc->image8.p);
-    if (rc != ZRT_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_rgb8, sc->image8.p, plan.n_floats, cudaMemcpyDeviceToHost, sc->stream));
-    unsigned long long h_counters[6];
-    CUDA_TRY(cudaMemcpyAsync(h_counters, sc->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, sc->stream));
-    CUDA_TRY(cudaEventRecord(sc->ev[3], sc->stream));
-    CUDA_TRY(cudaStreamSynchronize(sc->stream));
-    if (counters) {
-        counters->recursion_depth_hits = h_counters[0];
-        counters->reflections = h_counters[1];
-        counters->background_hits = h_counters[2];
-        counters->pixels_processed = h_counters[3];
-        counters->samples_processed = h_counters[4];
-        counters->rays_processed = h_counters[5];
-    }
-    if (timing) {
-        float k = 0, r = 0, tot = 0;
-        cudaEventElapsedTime(&k, sc->ev[0], sc->ev[1]);
-        cudaEventElapsedTime(&r, sc->ev[1], sc->ev[2]);
-        cudaEventElapsedTime(&tot, sc->ev[0], sc->ev[3]);
-        timing->prepare_ms = prep_now;
-        timing->kernel_ms = k;
-        timing->resolve_ms = r;
-        timing->total_ms = tot;
-        timing->launches = launches;
-        timing->bvh_nodes = (uint32_t)rep->info.nodes.size();
-    }
-    return ZRT_OK;
+    return renderToHost(sc, camera, params, nullptr, out_rgb8, counters, timing);
 }
 
 int zrt_render_device(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, float *d_rgb,
@@ -713,14 +734,20 @@ int zrt_render_device(zrt_scene *sc, const zrt_camera *camera, const zrt_params 
     rc = makePlan(sc, camera, params, rep, &plan);
     if (rc != ZRT_OK) return rc;
     uint32_t launches = 0;
-    return enqueueRender(sc, plan, d_rgb, reinterpret_cast<unsigned long long *>(d_counters),
-                         static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, &launches);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = enqueueRender(sc, plan, d_rgb, reinterpret_cast<unsigned long long *>(d_counters), st, nullptr, nullptr, nullptr,
+                       &launches);
+    if (rc != ZRT_OK) return rc;
+    CUDA_TRY(cudaEventRecord(sc->ev_user, st));
+    sc->user_pending = true;
+    return ZRT_OK;
 }
 
 int zrt_primary_hits(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, int jitter,
                      uint32_t *surface_id, float *t) {
     int rc = requireDevice(sc);
     if (rc != ZRT_OK) return rc;
+    quiesce(sc);
     if (!surface_id || !t) return fail(ZRT_ERR_INVALID, "output pointers are NULL");
     if (!params) return fail(ZRT_ERR_INVALID, "params is NULL");
     DevRep *rep = nullptr;
@@ -765,6 +792,14 @@ static const FlatBvh *hostBvh(zrt_scene *sc, uint32_t flags) {
 
 uint64_t zrt_scene_launch_count(const zrt_scene *sc) { return sc ? sc->launch_count : 0; }
 
+uint32_t zrt_build_features(void) {
+#ifdef ZRT_EXPERIMENTS
+    return ZRT_FEATURE_EXPERIMENTS;
+#else
+    return 0;
+#endif
+}
+
 int zrt_scene_bvh_info(zrt_scene *sc, uint32_t flags, zrt_bvh_info *out) {
     if (!sc || !out) return fail(ZRT_ERR_INVALID, "NULL argument");
     const FlatBvh *b = hostBvh(sc, flags);
@@ -791,6 +826,7 @@ int zrt_scene_bvh_order(zrt_scene *sc, uint32_t *order, uint8_t *visible) {
 int zrt_trace_statistics(zrt_scene *sc, const zrt_camera *camera, const zrt_params *params, zrt_trace_stats *out) {
     int rc = requireDevice(sc);
     if (rc != ZRT_OK) return rc;
+    quiesce(sc);
     if (!out || !params) return fail(ZRT_ERR_INVALID, "NULL argument");
     DevRep *rep = nullptr;
     rc = selectRep(sc, params, &rep);

@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
+#include <memory>
 #include <string>
 #include <system_error>
 #include <thread>
@@ -143,24 +145,54 @@ struct KParams {
     // packed operands of primary_direction_raw: (x, y) pairs of the camera vectors, (width, height) and reciprocals
     float pk_ll[2], pk_h[2], pk_v[2], pk_no[2], pk_nwh[2], pk_rcp[2];
     uint32_t two_paths; // 1: k_trace_x2
+    uint32_t pool;      // spheres-only scenes: slots per warp of k_trace_pool (0 = k_trace)
+    uint32_t inl_kinds; // ZRT_MATERIAL_* of inline sphere i in bits 2i, 2i+1
 };
 
 enum TraceMode { MODE_SPHERES = 0, MODE_LIST = 1, MODE_BVH = 2 };
 
-// A helper thread that cannot fail: if the system refuses another thread, the work runs on the caller's.
+// A helper thread that cannot fail to start (if the system refuses another thread, the work runs on the caller's) and
+// whose exceptions come back to the joining thread: nothing may reach std::terminate below the C ABI.
 struct Worker {
     std::thread t;
+    std::shared_ptr<std::exception_ptr> err;
     Worker() = default;
+    Worker(Worker &&) = default;
+    Worker &operator=(Worker &&o) {
+        if (this != &o) {
+            finish();
+            t = std::move(o.t);
+            err = std::move(o.err);
+        }
+        return *this;
+    }
     template <class F>
-    explicit Worker(F f) {
+    explicit Worker(F f) : err(std::make_shared<std::exception_ptr>()) {
+        auto slot = err;
+        auto body = [f, slot]() mutable {
+            try {
+                f();
+            } catch (...) {
+                *slot = std::current_exception();
+            }
+        };
         try {
-            t = std::thread(f);
+            t = std::thread(body);
         } catch (const std::system_error &) {
-            f();
+            body();
         }
     }
-    void join() {
+    ~Worker() { finish(); } // a caller that unwinds past a running worker waits for it instead of terminating
+    void finish() noexcept {
         if (t.joinable()) t.join();
+    }
+    void join() { // rethrows what the worker threw
+        finish();
+        if (err && *err) {
+            std::exception_ptr e = *err;
+            *err = nullptr;
+            std::rethrow_exception(e);
+        }
     }
 };
 

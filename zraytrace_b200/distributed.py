@@ -63,6 +63,12 @@ def render_distributed(dev_scene, camera, params, accum=None, counters=None, gro
         counters = torch.zeros(6, dtype=torch.int64, device=dev)
     p = rank_params(params, rank, world)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    dev_scene.render_device(camera, p, accum.data_ptr(), counters.data_ptr(), stream)
+    if p.sample_begin == p.sample_end:
+        # fewer samples than ranks: this rank has nothing to trace.  (0, 0) must not reach the C ABI, where it
+        # means "all samples" (zrt.h: sample_begin / sample_end)
+        accum.zero_()
+        counters.zero_()
+    else:
+        dev_scene.render_device(camera, p, accum.data_ptr(), counters.data_ptr(), stream)
     reduce_and_scale(accum, counters, params.samples_per_pixel, group)
     return accum, counters

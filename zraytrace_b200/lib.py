@@ -42,6 +42,7 @@ def lib():
         L.zrt_scene_bvh_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.zrt_scene_launch_count.argtypes = [C.c_void_p]
         L.zrt_scene_launch_count.restype = C.c_uint64
+        L.zrt_build_features.restype = C.c_uint32
         L.zrt_trace_statistics.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), P(A.TraceStats)]
         L.zrt_selftest.argtypes = [C.c_int, P(C.c_uint64)]
         L.zrt_measure_peaks.argtypes = [C.c_int, P(C.c_double), C.c_int]
@@ -59,6 +60,11 @@ def _check(rc):
 
 def device_count():
     return lib().zrt_device_count()
+
+
+def has_experiments():
+    """True if the library was built with EXPERIMENTS=1 (k_trace_sorted / k_trace_x2 compiled in)."""
+    return bool(lib().zrt_build_features() & A.ZRT_FEATURE_EXPERIMENTS)
 
 
 class HostImage:
