@@ -7,7 +7,9 @@ ranks, one NCCL reduce of the fp32 accumulators).  rays = the reference's `rays_
 (raytrace.zig:69).  See DESIGN.md "Measurement" for every field of the JSON line.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl zrt|reference]
-  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU)
+Without torchrun, --gpus N > 1 drives the N devices from this ONE process (zrt_multi_create: ncclCommInitAll).
+Either way the per-step path is libzrt only: zrt_multi_render = trace + ncclReduce + 1/spp (+ copy home for e2e).
 """
 import argparse
 import json
@@ -23,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-from zraytrace_b200 import _abi as A  # noqa: E402
+from zraytrace_b200 import _abi as A  # noqa: E402  (ctypes structs only: does not load libzrt.so)
 
 # workload -> (scene index, variant, width, height, spp, depth, aspect, x_limit, bvh flags, description)
 WORKLOADS = {
@@ -52,52 +54,99 @@ def algorithmic_ops(stats, counters):
             + OPS["dielectric_refract"] * s["dielectric_refract"] + OPS["background"] * s["background"])
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_trace launch at the bench size, from the committed
-# `ncu --set full` capture named here (a number measured under a profiler is only ever used for this field)
-NCU_TRAFFIC = {"c5": {"bytes": 3894528 + 44411136, "source": "profiles/r1_v10_c5_k_trace.txt (1 GPU, 1000 spp)"}}
+# Per-launch numbers of the dominant kernel from the committed `ncu --set full` captures named here (a number measured
+# under a profiler is only ever used for these fields): dram bytes read + written, l1tex / lts bytes, issue-slot
+# utilisation and active lanes per instruction.  Filled from profiles/ by hand after each capture.
+NCU = {
+    "c5": {"traffic": 3894528 + 44411136, "source": "profiles/r1_v10_c5_k_trace.txt (1 GPU, 1000 spp, k_trace<0,7>)"},
+}
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and clock-event (throttle) reasons of the listed GPUs, sampled through NVML (what nvidia-smi
+    reads) every few ms from a thread that is started at least a second before the timed region; only the samples
+    whose timestamps fall inside the region count.  Falls back to `nvidia-smi -lms` if pynvml is missing."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_indices):
-        self.idx = set(gpu_indices)
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, gpu_indices, period_s=0.005):
+        self.idx = list(gpu_indices)
+        self.period = period_s
+        self.samples = []  # (t, gpu, sm_mhz, max_mhz, power_w, reasons_mask)
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
+        self.backend = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            hs = [(i, pynvml.nvmlDeviceGetHandleByIndex(i)) for i in self.idx]
+            mx = {i: pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM) for i, h in hs}
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
 
-    def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        self.p.wait()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
-        for line in self.f:
+            def loop():
+                while not self._stop.is_set():
+                    for i, h in hs:
+                        try:
+                            self.samples.append((time.perf_counter(), i, pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                                 mx[i], pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons(h))))
+                        except Exception:
+                            pass
+                    time.sleep(self.period)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            self.backend = "nvml"
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self._f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self._smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=self._f, stderr=subprocess.DEVNULL)
+            self.backend = "nvidia-smi"
+        except OSError:
+            self._smi = None
+
+    def stop(self, t0=None, t1=None):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            rows = [s for s in self.samples if t0 is None or t0 <= s[0] <= t1]
+            sm = [s[2] for s in rows]
+            masks = [s[5] for s in rows]
+            reasons = sorted({n for n, bit in self.REASONS for mk in masks if mk & bit})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((s[3] for s in rows), default=None),
+                    "reasons": reasons, "samples": len(rows), "samples_total": len(self.samples),
+                    "power_w_max": max((s[4] for s in rows), default=None), "backend": "nvml", "period_ms": 1e3 * self.period}
+        if self._smi is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"], "samples": 0}
+        time.sleep(0.1)
+        self._smi.terminate()
+        self._smi.wait()
+        self._f.flush()
+        self._f.seek(0)
+        sm, mx, power, reasons = [], [], [], set()
+        for line in self._f:
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9 or not c[0].isdigit() or int(c[0]) not in self.idx:
+            if len(c) < 8 or not c[0].isdigit() or int(c[0]) not in self.idx:
                 continue
             try:
                 sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
+        os.unlink(self._f.name)
         busy = [s for s, p in zip(sm, power) if p > 250.0] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+                "reasons": sorted(reasons), "samples": len(busy), "samples_total": len(sm),
+                "power_w_max": max(power) if power else None, "backend": "nvidia-smi -lms 50 (samples under load, no timestamps)"}
 
 
 def load_peaks():
@@ -112,6 +161,20 @@ def params_for(wl, **kw):
                          seed=42, **kw)
 
 
+def oracle_scene(wl_name, wl):
+    """The workload's scene for the CPU legs, built WITHOUT libzrt where a pure-Python builder exists
+    (tests/scenes_py.py restates scenes.zig); c4's subdivided mesh only exists in the C++ host mirror."""
+    from tests import scenes_py
+    make = {"c1": scenes_py.three_balls, "c5": scenes_py.three_balls, "c2": scenes_py.teapot_and_ball,
+            "c3": lambda: scenes_py.bunny_and_ball(dielectric=True)}.get(wl_name)
+    if make is not None:
+        sc, cam = make()
+        return sc, cam, "tests/scenes_py (pure Python)"
+    from zraytrace_b200 import host
+    hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0))
+    return hs, hs.camera, "zraytrace_b200.host (C++ host mirror inside libzrt: c4's subdivided mesh has no Python builder)"
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, wl_name, wl):
     """--impl reference: the reference's CPU path (the oracle port; the Zig original cannot be built in this
@@ -120,10 +183,9 @@ def run_reference(args, wl_name, wl):
     if rank != 0:
         return
     from oracle import zro_py
-    from zraytrace_b200 import host
 
     cores = os.cpu_count() or 1
-    hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0))
+    sc, cam, scene_src = oracle_scene(wl_name, wl)
     # bounded sample: same image plane and depth, spp reduced so one step is a few seconds on this host
     target_rays = 6e6 * cores * (1.0 if wl_name in ("c1", "c5") else 0.02)
     rays_per_sample = 2.15 if wl_name in ("c1", "c5") else 1.6
@@ -132,7 +194,7 @@ def run_reference(args, wl_name, wl):
     times, rays = [], 0
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        _, c, _ = zro_py.render(hs, hs.camera, p, rng=zro_py.RNG_CTR, traversal=zro_py.TRAVERSAL_REF,
+        _, c, _ = zro_py.render(sc, cam, p, rng=zro_py.RNG_CTR, traversal=zro_py.TRAVERSAL_REF,
                                 math=zro_py.MATH_LIBM, threads=cores)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
@@ -140,48 +202,150 @@ def run_reference(args, wl_name, wl):
             rays = c.rays_processed
     total = sum(times)
     value = rays * len(times) / total / 1e6
+    # the literal single-thread figure (sequential Xoroshiro stream, as the reference really runs), bounded to ~5 s
+    heavy = wl_name not in ("c1", "c5")
+    div = (16 if wl_name == "c4" else 4) if heavy else 4
+    p1 = A.make_params(wl["w"] // div, wl["h"] // div, 1 if heavy else 8, wl["depth"], bvh=True, x_limit=wl.get("x_limit", 0), seed=42)
+    t0 = time.perf_counter()
+    _, c1, _ = zro_py.render(sc, cam, p1, rng=zro_py.RNG_REF, traversal=zro_py.TRAVERSAL_REF, math=zro_py.MATH_LIBM)
+    one_thread = c1.rays_processed / (time.perf_counter() - t0) / 1e6
     sample = (f"oracle port of the reference CPU path (Zig original not buildable here), {wl['w']}x{wl['h']} plane, "
               f"{spp} spp per step instead of {wl['spp']}, depth {wl['depth']}, {cores} threads over scanlines, "
-              f"literal aabb.zig traversal, glibc transcendentals")
+              f"literal aabb.zig traversal, glibc transcendentals; scene from {scene_src}")
     line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl_name}: {wl['desc']}", "spp_per_step": spp},
-            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
+                             "single_thread_literal": {"value": one_thread, "unit": "Mrays/s", "cores": 1,
+                                                       "sample": f"sequential Xoroshiro128+ stream, {p1.width}x{p1.height} plane, "
+                                                                 f"{p1.samples_per_pixel} spp: how the reference itself runs (README.md:11)"}},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-# ------------------------------------------------------------------------------------------- CPU baseline leg
-def cpu_baseline(wl_name, wl, hs):
+# ------------------------------------------------------------------------------------------- CPU legs of our arm
+def algorithmic_model(wl_name, wl):
+    """Event counts of the oracle (interval-carrying traversal of the REFERENCE tree, counter RNG) on a bounded sample of
+    the workload -> algorithmic FP32 ops and bytes per ray.  All host cores, about a second."""
+    from oracle import zro_py
+
+    sc, cam, _ = oracle_scene(wl_name, wl)
+    heavy = wl_name not in ("c1", "c5")
+    div = (8 if wl_name == "c4" else 2) if heavy else 1
+    spp = 2 if not heavy else 4
+    p = A.make_params(wl["w"] // div, wl["h"] // div, spp, wl["depth"], bvh=True, x_limit=wl.get("x_limit", 0), seed=42)
+    _, c, st = zro_py.render(sc, cam, p, rng=zro_py.RNG_CTR, traversal=zro_py.TRAVERSAL_TIGHT, threads=os.cpu_count() or 1)
+    ops_per_ray = algorithmic_ops(st.as_dict(), c.as_dict()) / c.rays_processed
+    bytes_per_ray = (64 * st.box_passes + 48 * st.triangle_tests + 16 * st.sphere_tests
+                     + 12 * c.samples_processed + 4 * st.texture_lookups) / c.rays_processed
+    return ops_per_ray, bytes_per_ray, f"{p.width}x{p.height} plane at {spp} spp, {c.rays_processed} rays"
+
+
+def cpu_baseline(wl_name, wl):
     """Oracle timed on ONE host core in its most literal mode (sequential Xoroshiro stream, libm, literal
     traversal): the reference is single-threaded (README.md:11).  Bounded sample, ~10-20 s."""
     from oracle import zro_py
 
+    sc, cam, _ = oracle_scene(wl_name, wl)
     heavy = wl_name not in ("c1", "c5")
     spp = 1 if heavy else max(1, min(wl["spp"], int(60e6 / (wl["w"] * wl["h"] * 2.15))))
     div = 16 if wl_name == "c4" else 4  # literal aabb.zig traversal visits ~10^3 nodes per ray (SURVEY Q4)
     w, h = (wl["w"] // div, wl["h"] // div) if heavy else (wl["w"], wl["h"])
     p = A.make_params(w, h, spp, wl["depth"], bvh=True, x_limit=wl.get("x_limit", 0), seed=42)
     t0 = time.perf_counter()
-    _, c, st = zro_py.render(hs, hs.camera, p, rng=zro_py.RNG_REF, traversal=zro_py.TRAVERSAL_REF, math=zro_py.MATH_LIBM)
+    _, c, st = zro_py.render(sc, cam, p, rng=zro_py.RNG_REF, traversal=zro_py.TRAVERSAL_REF, math=zro_py.MATH_LIBM)
     dt = time.perf_counter() - t0
-    # event counts for the algorithmic-op model come from the tight traversal (the reference's own visit
-    # counts include the Q4 defect and are not the algorithmic figure)
-    if heavy:
-        _, c2, st2 = zro_py.render(hs, hs.camera, p, rng=zro_py.RNG_CTR, traversal=zro_py.TRAVERSAL_TIGHT)
-    else:
-        c2, st2 = c, st
-    ops_per_ray = algorithmic_ops(st2.as_dict(), c2.as_dict()) / c2.rays_processed
-    bytes_per_ray = (64 * st2.box_passes + 48 * st2.triangle_tests + 16 * st2.sphere_tests
-                     + 12 * c2.samples_processed + 4 * st2.texture_lookups) / c2.rays_processed
     return {"value": c.rays_processed / dt / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
             "sample": (f"oracle port, single thread, sequential Xoroshiro128+ stream, glibc math, literal aabb.zig traversal; "
                        f"{w}x{h} plane at {spp} spp (full workload is {wl['w']}x{wl['h']} at {wl['spp']} spp), {dt:.1f} s"),
-            "rays_per_sample": c.rays_processed / c.samples_processed}, ops_per_ray, bytes_per_ray
+            "rays_per_sample": c.rays_processed / c.samples_processed}
 
 
 # ------------------------------------------------------------------------------------------- our arm
+def roofline_for(wl_name, kernel_name, kernel_ms, rays_launch, ops_per_ray, bytes_per_ray, model_sample, peaks, stats=None):
+    """The `roofline` object of one workload: the bound that applies, algorithmic work per launch / kernel time."""
+    peaks_file, peaks_src = load_peaks()
+    ncu = NCU.get(wl_name, {})
+    common = {"kernel": kernel_name, "kernel_ms": kernel_ms, "rays_per_launch": rays_launch,
+              "algorithmic_ops_per_ray": ops_per_ray, "algorithmic_bytes_per_ray": bytes_per_ray, "model_sample": model_sample,
+              "traffic": ncu.get("traffic"), "traffic_source": ncu.get("source"), "k0": peaks,
+              "hbm_peak_gbs": peaks_file.get("hbm_gbs"), "hbm_peak_source": peaks_src,
+              "mrays_per_s_kernel_only": rays_launch / (kernel_ms * 1e-3) / 1e6}
+    for k in ("issue_active_pct", "active_lanes", "l1tex_bytes", "lts_bytes"):
+        if k in ncu:
+            common["ncu_" + k] = ncu[k]
+    if wl_name in ("c2", "c3", "c4"):
+        # BVH workloads: the data (<= 36 MB of nodes and triangle planes) lives in L1/L2, HBM is idle; the byte side is the
+        # ALGORITHMIC traffic of SURVEY §8(d) - the oracle's interval-carrying traversal of the REFERENCE tree - against
+        # the measured L2 -> SM bandwidth.  What the device's SAH tree saves on top is reported beside it (`device_*`),
+        # and what actually limits these kernels (issue slots at 10-20 active lanes) is in the ncu_* fields.
+        achieved = bytes_per_ray * rays_launch / (kernel_ms * 1e-3) / 1e9
+        peak = peaks["l2_read_gbs"]
+        r = {"bound": "l2", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+             "peak_source": "L2-resident 128-bit read bandwidth measured in this run by zrt_measure_peaks (MEASURED_PEAKS.json "
+                            "has no L2 figure)"}
+        if stats is not None:
+            dev_bytes = (64 * stats.node_visits + 48 * stats.triangle_tests + 32 * stats.sphere_tests + 12 * stats.samples
+                         + 4 * stats.texture_lookups) / max(stats.rays, 1)
+            r["device_bytes_per_ray_sah_tree"] = dev_bytes
+            r["device_events_per_ray"] = {"node_visits": stats.node_visits / max(stats.rays, 1),
+                                          "triangle_tests": stats.triangle_tests / max(stats.rays, 1),
+                                          "sphere_tests": stats.sphere_tests / max(stats.rays, 1)}
+        r.update(common)
+        return r
+    achieved = ops_per_ray * rays_launch / (kernel_ms * 1e-3) / 1e12
+    peak = peaks["fp32_nofma_ops"] / 1e12
+    r = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+         "peak_source": "measured in this run by zrt_measure_peaks (FMUL/FADD chains, no FMA credit: parity forbids "
+                        "contraction); MEASURED_PEAKS.json has no FP32-issue figure"}
+    r.update(common)
+    return r
+
+
+def kernel_name_for(wl_name, flags):
+    if wl_name in ("c1", "c5"):
+        return "k_trace_pool<7,N>" if flags & A.ZRT_FLAG_KERNEL_POOL else "k_trace<SPHERES,7>"
+    return "k_trace_ws / k_trace<BVH>"
+
+
+def side_configs(Z, host, peaks, flags):
+    """c1..c4 at N = 1, a few steps each: the other BASELINE configurations in the driver's record."""
+    out = {}
+    for name in ("c1", "c2", "c3", "c4"):
+        wl = WORKLOADS[name]
+        try:
+            hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0)).pin()
+            p = params_for(wl, flags=flags if name == "c1" else 0)
+            with Z.HostImage((wl["h"], wl["w"], 3)) as him:
+                with Z.Scene(hs, device=0) as sc:
+                    for _ in range(3):
+                        sc.render(hs.camera, p, out=him.array)
+                    ks, rays = [], 0
+                    for _ in range(3):
+                        _, c, tm = sc.render(hs.camera, p, out=him.array)
+                        ks.append(tm.kernel_ms + tm.resolve_ms)
+                        rays = c.rays_processed
+                    stats = sc.trace_statistics(hs.camera, p) if name != "c1" else None
+                e2e = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    with Z.Scene(hs, device=0) as sc2:
+                        sc2.render(hs.camera, p, out=him.array)
+                    e2e.append(time.perf_counter() - t0)
+            ops, byts, sample = algorithmic_model(name, wl)
+            ms = float(np.mean(ks))
+            rf = roofline_for(name, kernel_name_for(name, p.flags), ms, rays, ops, byts, sample, peaks, stats)
+            out[name] = {"workload": wl["desc"], "ms": ms, "Mrays/s": rays / ms / 1e3, "bound": rf["bound"], "frac": rf["frac"],
+                         "e2e_ms": 1e3 * float(np.mean(e2e)), "rays_per_step": rays,
+                         "algorithmic_ops_per_ray": ops, "algorithmic_bytes_per_ray": byts,
+                         "device_bytes_per_ray_sah_tree": rf.get("device_bytes_per_ray_sah_tree")}
+            hs.close()
+        except Exception as e:  # a side config must never cost the headline line
+            out[name] = {"error": repr(e)}
+    return out
+
+
 def run_zrt(args, wl_name, wl):
     import torch
     import torch.distributed as dist
@@ -190,166 +354,153 @@ def run_zrt(args, wl_name, wl):
     from zraytrace_b200 import host
     from zraytrace_b200 import lib as Z
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torchrun = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    procs = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if Z.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible; libzrt has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world = procs if torchrun else max(1, args.gpus)       # ranks of the libzrt group = GPUs
+    my_devices = [local_rank] if torchrun else list(range(world))
+    if max(my_devices) >= Z.device_count():
+        raise SystemExit(f"bench.py: --gpus {world} but only {Z.device_count()} devices are visible")
+    torch.cuda.set_device(my_devices[0])
+    if torchrun:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     hs = host.HostScene(wl["scene"], variant=wl["variant"], aspect_ratio=wl.get("aspect", 1.0)).pin()  # page-locked texels
-    flags = A.ZRT_FLAG_BVH_REFERENCE if args.reftree else 0
+    flags = (A.ZRT_FLAG_BVH_REFERENCE if args.reftree else 0) | KERNEL_FLAGS[args.kernel]
     params = params_for(wl, flags=flags)
-    scene = Z.Scene(hs, device=local_rank)
-    accum = torch.empty((wl["h"], wl["w"], 3), dtype=torch.float32, device=dev)
-    counters = torch.zeros(6, dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    grp = D.create_group(hs, local_rank) if torchrun else Z.MultiScene(hs, devices=my_devices)
+    flush = [torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", d)) for d in my_devices]  # > 126 MB L2
+    peaks = Z.measure_peaks(my_devices[0]) if rank == 0 else None
 
-    peaks = Z.measure_peaks(local_rank) if rank == 0 else None
-
-    def barrier():
-        if world > 1:
+    def sync_all():
+        for d in my_devices:
+            torch.cuda.synchronize(d)
+        if torchrun:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
-    def step():
-        D.render_distributed(scene, hs.camera, params, accum, counters)
+    def flush_l2():
+        for f in flush:
+            f.zero_()
+        for d in my_devices:
+            torch.cuda.synchronize(d)
+        if torchrun:
+            dist.barrier()  # the ranks start a step together: rank 0's device time then measures the job, not the skew
 
     for _ in range(max(args.warmup, 3) if args.warmup else 0):
-        step()
-    barrier()
-    launches0 = scene.launch_count()
+        grp.render(hs.camera, params, to_host=False)
     sampler = ClockSampler(range(world)) if rank == 0 else None
     if sampler:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+        time.sleep(1.0)  # the sampler is up and has history before the timed region starts
+    sync_all()
+    launches0 = grp.launch_count()
     t_wall0 = time.perf_counter()
-    for s, e in ev:
-        flush.zero_()  # L2 flush between timed iterations, outside the per-step event pair
-        s.record()
-        step()
-        e.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if sampler else None
-    my_ms = sum(s.elapsed_time(e) for s, e in ev)
-    launches = scene.launch_count() - launches0
-    t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    cnt = counters.cpu().numpy().astype(np.uint64)  # valid on rank 0 (reduced)
-    rays_per_step = int(cnt[5])
+    dev_ms, kern_ms, cnt = [], [], None
+    for _ in range(args.steps):
+        flush_l2()  # L2 flush between timed iterations, outside the per-step device-event pair
+        _, c, tm = grp.render(hs.camera, params, to_host=False)  # device events on libzrt's stream: first launch -> scaled image
+        dev_ms.append(tm.total_ms)
+        kern_ms.append(tm.kernel_ms)
+        cnt = c
+    sync_all()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    launches = grp.launch_count() - launches0
+    t = torch.tensor([sum(dev_ms), float(launches)], dtype=torch.float64, device=torch.device("cuda", my_devices[0]))
+    if torchrun:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_ms, launches = float(tmax[0].item()), int(t[1].item())
+    else:
+        total_ms = float(t[0].item())
+    rays_per_step = int(cnt.rays_processed)  # valid on rank 0 (reduced)
 
-    # kernel-only time of this rank's share (for the roofline), CUDA events on the launching stream
+    # kernel-only time of rank 0's share (for the roofline), CUDA events on the launching stream
     p_rank = D.rank_params(params, rank, world)
+    dev0 = torch.device("cuda", my_devices[0])
+    accum = torch.empty((wl["h"], wl["w"], 3), dtype=torch.float32, device=dev0)
+    cnt_k = torch.zeros(6, dtype=torch.int64, device=dev0)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    cnt_k = torch.zeros(6, dtype=torch.int64, device=dev)
-    kernel_ms = []
-    for _ in range(3):
-        flush.zero_()
-        k0.record()
-        scene.render_device(hs.camera, p_rank, accum.data_ptr(), cnt_k.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        k1.record()
-        torch.cuda.synchronize()
-        kernel_ms.append(k0.elapsed_time(k1))
+    kernel_ms, stats = [], None
+    with Z.Scene(hs, device=my_devices[0]) as scene:
+        for i in range(4):
+            flush[0].zero_()
+            k0.record()
+            scene.render_device(hs.camera, p_rank, accum.data_ptr(), cnt_k.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            k1.record()
+            torch.cuda.synchronize()
+            if i:
+                kernel_ms.append(k0.elapsed_time(k1))
+        if wl_name in ("c2", "c3", "c4") and rank == 0:
+            stats = scene.trace_statistics(hs.camera, p_rank)
     kernel_ms = float(np.mean(kernel_ms))
     rays_rank = int(cnt_k.cpu().numpy().astype(np.uint64)[5])
 
-    # end to end through the public API with HOST buffers: scene upload (H2D), render, image + counters back
-    # (D2H) every step; N>1: every rank renders its share and rank 0 receives the reduced image
-    e2e_times = []
+    # end to end through the public API with HOST buffers, every step: scene flatten + upload (H2D), render, reduce,
+    # image + counters back into the caller's page-locked image (D2H)
     h2d = hs.upload_bytes() + 256
     d2h = wl["w"] * wl["h"] * 12 + 48
-    pinned = torch.empty((wl["h"], wl["w"], 3), dtype=torch.float32).pin_memory() if world > 1 else None
-    host_image = Z.HostImage((wl["h"], wl["w"], 3)) if world == 1 else None  # the caller's result image (zrt_pinned_alloc)
-    for i in range(2 + min(args.steps, 3)):
-        barrier()
+    host_image = Z.HostImage((wl["h"], wl["w"], 3)) if rank == 0 else None
+    e2e_times = []
+    for i in range(2 + args.steps):
+        sync_all()
         t0 = time.perf_counter()
         if world == 1:
-            with Z.Scene(hs, device=local_rank) as sc2:  # zrt_scene_create: flatten + H2D
-                img, c_e2e, _ = sc2.render(hs.camera, params, out=host_image.array)  # zrt_render: kernels + D2H into the host buffer
+            with Z.Scene(hs, device=my_devices[0]) as sc2:  # zrt_scene_create: flatten + H2D
+                sc2.render(hs.camera, params, out=host_image.array)  # zrt_render: kernels + D2H into the host buffer
         else:
-            with Z.Scene(hs, device=local_rank) as sc2:
-                a2, c2 = D.render_distributed(sc2, hs.camera, params)
-                if rank == 0:
-                    pinned.copy_(a2, non_blocking=True)
-                    c2.cpu()
-                torch.cuda.synchronize()
-        barrier()
+            grp.reload(hs)  # zrt_scene_create on every rank's device: flatten + H2D
+            grp.render(hs.camera, params, out=host_image.array if rank == 0 else None)
+        sync_all()
         if i >= 2:
             e2e_times.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_times))
 
     if rank != 0:
-        if world > 1:
+        if torchrun:
             dist.destroy_process_group()
         return
 
     value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
-    peaks_file, peaks_src = load_peaks()
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{wl_name}: {wl['desc']}", "parallelism": f"spp-split x{world} + 1 NCCL reduce",
-                       "rays_per_step": rays_per_step, "samples_per_step": int(cnt[4]),
+            "config": {"workload": f"{wl_name}: {wl['desc']}",
+                       "parallelism": f"spp-split x{world} + 1 ncclReduce (libzrt zrt_multi_render; "
+                                      + ("one process per GPU, torchrun" if torchrun else "one process drives all GPUs") + ")",
+                       "kernel": kernel_name_for(wl_name, flags),
+                       "rays_per_step": rays_per_step, "samples_per_step": int(cnt.samples_processed),
                        "l2": "256 MiB device memset between timed steps (outside the per-step event pairs); "
                              "scene data is <= a few MB and stays cache resident by design",
-                       "bvh": ("reference topology" if flags else "binned SAH over the reference's surviving primitives") if wl_name in ("c2", "c3", "c4") else "none (surface list)", "seed": 42,
-                       "wall_s_timed_region": t_wall},
+                       "timing": "per step: CUDA events on libzrt's stream, first launch -> reduced and scaled image on rank 0; "
+                                 "sum over steps, max over ranks",
+                       "bvh": ("reference topology" if args.reftree else "binned SAH over the reference's surviving primitives") if wl_name in ("c2", "c3", "c4") else "none (surface list)", "seed": 42,
+                       "trace_ms_per_step_slowest_rank": float(np.mean(kern_ms)), "nccl_version": Z.nccl_version() if world > 1 else None,
+                       "wall_s_timed_region": t_wall1 - t_wall0},
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": rays_per_step / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s, "steps": len(e2e_times),
                     "path": "zrt_scene_create (H2D: page-locked texels, pageable primitive arrays) + zrt_render into a page-locked host image (D2H) per step" if world == 1 else
-                            "zrt_scene_create + zrt_render_device + NCCL reduce + D2H per step"},
+                            "zrt_multi_reload (zrt_scene_create per rank) + zrt_multi_render (trace, ncclReduce, 1/spp, D2H into a page-locked host image) per step"},
             "published_reference": {"value": 3.47, "unit": "Mrays/s", "note": "README.md:49-61, unknown CPU, 1 thread"}}
-    cpu = None
+    ops_per_ray, bytes_per_ray, model_sample = algorithmic_model(wl_name, wl)
     if world == 1 and not args.no_cpu:
-        cpu, ops_per_ray, bytes_per_ray = cpu_baseline(wl_name, wl, hs)
-        line["cpu_baseline"] = cpu
-    else:
-        ops_per_ray = {"c1": 201.0, "c5": 200.94}.get(wl_name)  # measured by the cpu_baseline leg at N=1 (oracle events)
-        bytes_per_ray = None
-    is_bvh = wl_name in ("c2", "c3", "c4")
-    if is_bvh:
-        # byte side: event counts from the instrumented build of the same kernel on this rank's share
-        st = scene.trace_statistics(hs.camera, p_rank)
-        alg_bytes = (64 * st.node_visits + 48 * st.triangle_tests + 32 * st.sphere_tests + 12 * st.samples
-                     + 4 * st.texture_lookups)
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        peak = peaks["l2_read_gbs"]
-        line["roofline"] = {"bound": "l2", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "k_trace", "kernel_ms": kernel_ms, "rays_per_launch": rays_rank,
-                            "algorithmic_bytes_per_ray": alg_bytes / max(st.rays, 1),
-                            "events_per_ray": {"node_visits": st.node_visits / max(st.rays, 1),
-                                               "triangle_tests": st.triangle_tests / max(st.rays, 1),
-                                               "sphere_tests": st.sphere_tests / max(st.rays, 1)},
-                            "peak_source": "L2-resident 128-bit read bandwidth measured in this run by zrt_measure_peaks "
-                                           "(MEASURED_PEAKS.json has no L2 figure); scene data is L1/L2 resident, HBM is idle",
-                            "k0": peaks, "hbm_peak_gbs": peaks_file.get("hbm_gbs"), "hbm_peak_source": peaks_src,
-                            "fp32_ops_per_ray_reference_tree": ops_per_ray,
-                            "mrays_per_s_kernel_only": rays_rank / (kernel_ms * 1e-3) / 1e6}
-    elif ops_per_ray:
-        achieved = ops_per_ray * rays_rank / (kernel_ms * 1e-3) / 1e12
-        peak = peaks["fp32_nofma_ops"] / 1e12
-        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": NCU_TRAFFIC.get(wl_name, {}).get("bytes") if world == 1 else None,
-                            "traffic_source": NCU_TRAFFIC.get(wl_name, {}).get("source"),
-                            "kernel": "k_trace", "kernel_ms": kernel_ms, "rays_per_launch": rays_rank,
-                            "algorithmic_ops_per_ray": ops_per_ray, "algorithmic_bytes_per_ray": bytes_per_ray,
-                            "peak_source": "measured in this run by zrt_measure_peaks (FMUL/FADD chains, no FMA credit: "
-                                           "parity forbids contraction); MEASURED_PEAKS.json has no FP32-issue figure",
-                            "k0": peaks, "hbm_peak_gbs": peaks_file.get("hbm_gbs"), "hbm_peak_source": peaks_src,
-                            "mrays_per_s_kernel_only": rays_rank / (kernel_ms * 1e-3) / 1e6}
+        line["cpu_baseline"] = cpu_baseline(wl_name, wl)
+    line["roofline"] = roofline_for(wl_name, kernel_name_for(wl_name, flags), kernel_ms, rays_rank, ops_per_ray, bytes_per_ray,
+                                    model_sample, peaks, stats)
+    if world == 1 and wl_name == "c5" and not args.no_configs:
+        line["configs"] = side_configs(Z, host, peaks, flags)
     emit(line)
-    if world > 1:
+    if torchrun:
         dist.destroy_process_group()
 
 
+KERNEL_FLAGS = {"auto": 0, "thread": A.ZRT_FLAG_KERNEL_THREAD, "warp": A.ZRT_FLAG_KERNEL_WARP, "pool": A.ZRT_FLAG_KERNEL_POOL}
 _JSON_FD = None
 
 
@@ -375,8 +526,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="zrt", choices=["zrt", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=sorted(KERNEL_FLAGS), help="force a kernel variant (default: the library's choice)")
     ap.add_argument("--reftree", action="store_true", help="BVH workloads: traverse the reference topology, not the SAH tree")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c1..c4 side block of the default line")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

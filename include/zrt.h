@@ -34,7 +34,8 @@ enum {
     ZRT_ERR_NO_DEVICE = -2, /* no CUDA device: there is deliberately no CPU fallback */
     ZRT_ERR_CUDA = -3,      /* a CUDA runtime call failed, see zrt_last_error() */
     ZRT_ERR_OOM = -4,       /* host allocation failed (error.OutOfMemory in the reference) */
-    ZRT_ERR_IO = -5         /* asset file could not be read / written (host helpers only) */
+    ZRT_ERR_IO = -5,        /* asset file could not be read / written (host helpers only) */
+    ZRT_ERR_NCCL = -6       /* multi-GPU group: libnccl.so.2 could not be loaded, or an NCCL call failed */
 };
 
 /* ---- math PODs: vector.zig:22-26 (Vec3), base.zig:2 (BaseFloat = f32) ---- */
@@ -204,6 +205,36 @@ int zrt_render_rgb8(zrt_scene *scene, const zrt_camera *camera, const zrt_params
  * that the accumulators can be summed with one NCCL reduce without touching the host. */
 int zrt_render_device(zrt_scene *scene, const zrt_camera *camera, const zrt_params *params,
                       float *d_rgb, uint64_t *d_counters, void *stream);
+
+/* ---- multi-GPU: raytrace.render() over W devices (BASELINE.json north_star) -------------------------
+ * The scene is replicated on every device; rank g of W traces the global samples [g*spp/W, (g+1)*spp/W) of every
+ * pixel; the f32 accumulators are summed with ONE ncclReduce (plus one of the six u64 counters) over NVLink to
+ * rank 0, which applies the reference's 1/samples_per_pixel (raytrace.zig:157,182).  The RNG is keyed on the global
+ * sample index: the counters do not depend on W, the image only through the association of the f32 sum.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2") and only by these calls.
+ *   zrt_multi_create       one process drives n_devices GPUs (devices = NULL: 0..n-1): ncclCommInitAll.
+ *   zrt_multi_create_rank  one process per GPU: every process calls it with the same id (made by zrt_comm_id on one of
+ *                          them and distributed by the caller - MPI, torch.distributed, a file) and its own rank.
+ *   zrt_multi_render       zrt_render for the group.  Every process of the group calls it with the same arguments; image
+ *                          and counters arrive on the process that owns rank 0 (out_rgb may be NULL elsewhere, and on
+ *                          rank 0 to leave the image on the device: zrt_multi_image_device).  timing: kernel_ms = slowest
+ *                          local rank's trace, total_ms = first launch -> reduced, scaled image on the device.
+ * Callable from one host thread at a time per group. */
+typedef struct zrt_multi zrt_multi;
+#define ZRT_COMM_ID_BYTES 128
+int zrt_comm_id(uint8_t id[ZRT_COMM_ID_BYTES]);
+int zrt_multi_create(const zrt_scene_desc *desc, const int *devices, int n_devices, zrt_multi **out);
+int zrt_multi_create_rank(const zrt_scene_desc *desc, int device, const uint8_t id[ZRT_COMM_ID_BYTES], int rank, int world,
+                          zrt_multi **out);
+void zrt_multi_destroy(zrt_multi *group);
+/* A new scene for the same group (communicator and accumulators are kept): zrt_scene_create on every local device. */
+int zrt_multi_reload(zrt_multi *group, const zrt_scene_desc *desc);
+int zrt_multi_render(zrt_multi *group, const zrt_camera *camera, const zrt_params *params, float *out_rgb,
+                     zrt_counters *counters, zrt_timing *timing);
+int zrt_multi_world_size(const zrt_multi *group);
+uint64_t zrt_multi_launch_count(const zrt_multi *group);     /* libzrt kernels launched by the local ranks */
+const float *zrt_multi_image_device(const zrt_multi *group); /* rank 0's device copy of the last image (NULL elsewhere) */
+int zrt_nccl_version(void);                                  /* NCCL_VERSION_CODE of the loaded library, 0 if none */
 
 /* Optional pieces compiled into this build of the library. */
 enum { ZRT_FEATURE_EXPERIMENTS = 1u << 0 /* k_trace_sorted / k_trace_x2 (make EXPERIMENTS=1); without it their flags fail */ };

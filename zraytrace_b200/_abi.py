@@ -1,7 +1,8 @@
 """ctypes mirror of include/zrt.h (the C ABI of libzrt).  Field order and types must match the header."""
 import ctypes as C
 
-ZRT_OK, ZRT_ERR_INVALID, ZRT_ERR_NO_DEVICE, ZRT_ERR_CUDA, ZRT_ERR_OOM, ZRT_ERR_IO = 0, -1, -2, -3, -4, -5
+ZRT_OK, ZRT_ERR_INVALID, ZRT_ERR_NO_DEVICE, ZRT_ERR_CUDA, ZRT_ERR_OOM, ZRT_ERR_IO, ZRT_ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
+ZRT_COMM_ID_BYTES = 128
 ZRT_SURFACE_SPHERE, ZRT_SURFACE_TRIANGLE = 0, 1
 ZRT_MATERIAL_LAMBERTIAN, ZRT_MATERIAL_METAL, ZRT_MATERIAL_DIELECTRIC = 0, 1, 2
 ZRT_TEXTURE_COLOR, ZRT_TEXTURE_IMAGE = 0, 1

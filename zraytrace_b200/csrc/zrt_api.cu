@@ -13,7 +13,9 @@
 #include <string>
 #include <vector>
 
-#include "zrt_internal.h"
+#include <mutex>
+
+#include "zrt_scene.h"
 
 namespace zrt {
 uint32_t launch_trace(const KParams &P, int mode, cudaStream_t st);
@@ -29,122 +31,42 @@ void launch_peak_read(const float4 *src, size_t n4, int passes, float *out, int 
 
 using namespace zrt;
 
-namespace {
+namespace zrt {
 
-thread_local std::string g_error;
+static thread_local std::string g_error;
 
 int fail(int code, const std::string &msg) {
     g_error = msg;
     return code;
 }
-#define CUDA_TRY(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t _e = (expr);                                                                         \
-        if (_e != cudaSuccess)                                                                           \
-            return fail(ZRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
-    } while (0)
 
 // Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync) with the release
 // threshold raised, so creating and destroying scenes or scratch images does not pay cudaMalloc/cudaFree
 // (the 100+ ms spikes seen in the first end-to-end measurements) after the first use.
 cudaStream_t g_alloc_stream(int device) {
+    static std::mutex mu;
     static cudaStream_t streams[64] = {};
     if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
     if (!streams[device]) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             unsigned long long keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
         cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+        cudaSetDevice(cur);
     }
     return streams[device];
 }
 
-template <class T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    // H2D on `st`: ordered before everything enqueued on `st` afterwards.  For pageable memory the call returns once
-    // the source has been staged, so the caller may free `src` right away; the scene builders synchronise `st` once
-    // at the end, which makes the data visible to every other stream as well.
-    cudaError_t upload(const std::vector<T> &v, cudaStream_t st) { return upload(v.data(), v.size(), st); }
-    cudaError_t upload(const T *src, size_t count, cudaStream_t st) {
-        cudaError_t e = reserve(count);
-        if (e != cudaSuccess || count == 0) return e;
-        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st);
-    }
-    cudaError_t reserve(size_t count) {
-        if (count <= n) return cudaSuccess;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaStream_t st = g_alloc_stream(dev);
-        release();
-        cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st); // usable from any stream afterwards
-        if (e == cudaSuccess) n = count;
-        else p = nullptr;
-        return e;
-    }
-    void release() {
-        if (p) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaFreeAsync(p, g_alloc_stream(dev));
-        }
-        p = nullptr;
-        n = 0;
-    }
-};
+} // namespace zrt
 
-// one device-resident representation of the scene (list order, reference-tree order, or SAH tree)
-struct DevRep {
-    bool ready = false;
-    int mode = MODE_LIST;
-    DevBuf<DevSphere> spheres;
-    DevBuf<float4> triA, triE1, triE2;
-    DevBuf<TriMeta> triMeta;
-    DevBuf<uint32_t> list;
-    DevBuf<DevNode> nodes;
-    std::vector<DevSphere> h_spheres;
-    uint32_t n_spheres = 0, n_list = 0, root = REF_EMPTY;
-    FlatBvh info;
-    float prepare_ms = 0.0f;
-    void release() {
-        spheres.release(); triA.release(); triE1.release(); triE2.release();
-        triMeta.release(); list.release(); nodes.release();
-        ready = false;
-    }
-};
 
-} // namespace
-
-struct zrt_scene {
-    int device = -1;
-    HostScene host;
-    bool all_spheres = false;
-    DevBuf<DevMaterial> mats;
-    std::vector<DevBuf<uint8_t>> d_texels;
-    DevRep rep_list, rep_bvh, rep_sah;
-    FlatBvh host_bvh[2]; // host-only inspection (device == -1)
-    bool host_bvh_ready[2] = {false, false};
-    // scratch owned by the scene
-    DevBuf<float> part, image;
-    DevBuf<uint8_t> image8;
-    DevBuf<unsigned long long> counters;
-    DevBuf<uint32_t> hit_id, work;
-    DevBuf<float> hit_t;
-    uint64_t launch_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    // zrt_render_device enqueues on the CALLER's stream while the scene's buffers are freed on the allocation stream:
-    // ev_user marks the end of the last such render, and everything that frees, grows or reuses a scene buffer waits
-    // for it first (quiesce / orderAfterUser).  A scene is used from one stream at a time.
-    cudaEvent_t ev_user = nullptr;
-    bool user_pending = false;
-};
-
-namespace {
+namespace zrt {
 
 uint32_t packMaterial(const HostScene &hs, uint32_t m) {
     const zrt_material &mat = hs.materials[m];
@@ -256,84 +178,90 @@ int uploadMaterials(zrt_scene *sc) {
     return ZRT_OK;
 }
 
-int buildListRep(zrt_scene *sc, DevRep &r) {
-    const HostScene &hs = sc->host;
+// ---- flattening (host, once per scene and representation) and upload (once per device) ----------------------------
+static std::shared_ptr<HostRep> flattenList(const HostScene &hs, bool all_spheres) {
+    auto h = std::make_shared<HostRep>();
     const uint32_t n = (uint32_t)hs.surfaces.size();
-    std::vector<uint32_t> list(n);
-    std::vector<float4> A(n), E1(n), E2(n);
-    std::vector<TriMeta> meta(n);
-    r.h_spheres.clear();
+    h->list.resize(n);
+    if (hs.triangles.size()) { h->A.resize(n); h->E1.resize(n); h->E2.resize(n); h->meta.resize(n); }
     for (uint32_t i = 0; i < n; i++) {
         if (hs.surfaces[i].kind == ZRT_SURFACE_SPHERE) {
-            list[i] = REF_LEAF | REF_SPHERE | (uint32_t)r.h_spheres.size();
-            r.h_spheres.push_back(makeSphere(hs, i, i));
+            h->list[i] = REF_LEAF | REF_SPHERE | (uint32_t)h->spheres.size();
+            h->spheres.push_back(makeSphere(hs, i, i));
+            if (hs.triangles.size()) { h->A[i] = h->E1[i] = h->E2[i] = float4{0, 0, 0, 0}; h->meta[i] = TriMeta{0, i}; }
         } else {
-            list[i] = REF_LEAF | i; // triangle planes are indexed by list position
-            makeTriangle(hs, i, &A[i], &E1[i], &E2[i], &meta[i]);
+            h->list[i] = REF_LEAF | i; // triangle planes are indexed by list position
+            makeTriangle(hs, i, &h->A[i], &h->E1[i], &h->E2[i], &h->meta[i]);
         }
     }
-    r.n_spheres = (uint32_t)r.h_spheres.size();
-    r.n_list = n;
-    r.mode = (sc->all_spheres && n <= MAX_INLINE_SPHERES && n > 0) ? MODE_SPHERES : MODE_LIST;
-    cudaStream_t st = sc->stream;
-    CUDA_TRY(r.spheres.upload(r.h_spheres, st));
-    CUDA_TRY(r.list.upload(list, st));
-    if (hs.triangles.size()) {
-        CUDA_TRY(r.triA.upload(A, st)); CUDA_TRY(r.triE1.upload(E1, st)); CUDA_TRY(r.triE2.upload(E2, st));
-        CUDA_TRY(r.triMeta.upload(meta, st));
-    }
-    CUDA_TRY(cudaStreamSynchronize(st));
-    r.ready = true;
-    return ZRT_OK;
+    h->n_list = n;
+    h->mode = (all_spheres && n <= MAX_INLINE_SPHERES && n > 0) ? MODE_SPHERES : MODE_LIST;
+    return h;
 }
 
-int buildBvhRep(zrt_scene *sc, DevRep &r, bool sah) {
-    const HostScene &hs = sc->host;
-    build_flat_bvh(hs, sah, &r.info);
+static std::shared_ptr<HostRep> flattenBvh(const HostScene &hs, bool sah) {
+    auto h = std::make_shared<HostRep>();
+    build_flat_bvh(hs, sah, &h->info);
     BuildLap lap;
-    if (r.info.max_depth + 2 >= (uint32_t)TRAVERSAL_STACK)
-        return fail(ZRT_ERR_INVALID, "BVH deeper than the traversal stack; drop ZRT_FLAG_BVH_REFERENCE");
-    const uint32_t slots = (uint32_t)r.info.slot_surface.size();
-    std::vector<float4> A(slots), E1(slots), E2(slots);
-    std::vector<TriMeta> meta(slots);
-    r.h_spheres.clear();
+    const uint32_t slots = (uint32_t)h->info.slot_surface.size();
+    h->A.resize(slots); h->E1.resize(slots); h->E2.resize(slots); h->meta.resize(slots);
     // sphere_seq in zrt_flatten.cpp numbers spheres in surface-list order
     std::vector<uint32_t> slot_of(hs.surfaces.size(), 0);
-    for (uint32_t s = 0; s < slots; s++) slot_of[r.info.slot_surface[s]] = s;
+    for (uint32_t s = 0; s < slots; s++) slot_of[h->info.slot_surface[s]] = s;
     for (uint32_t i = 0; i < hs.surfaces.size(); i++)
-        if (hs.surfaces[i].kind == ZRT_SURFACE_SPHERE) r.h_spheres.push_back(makeSphere(hs, i, slot_of[i]));
-    parallelFor(slots, 16384, [&](size_t begin, size_t end) {
+        if (hs.surfaces[i].kind == ZRT_SURFACE_SPHERE) h->spheres.push_back(makeSphere(hs, i, slot_of[i]));
+    HostRep *hp = h.get();
+    parallelFor(slots, 16384, [&hs, hp](size_t begin, size_t end) {
         for (size_t s = begin; s < end; s++) {
-            const uint32_t surf = r.info.slot_surface[s];
-            if (hs.surfaces[surf].kind == ZRT_SURFACE_TRIANGLE) makeTriangle(hs, surf, &A[s], &E1[s], &E2[s], &meta[s]);
-            else { A[s] = E1[s] = E2[s] = float4{0, 0, 0, 0}; meta[s] = TriMeta{0, surf}; }
+            const uint32_t surf = hp->info.slot_surface[s];
+            if (hs.surfaces[surf].kind == ZRT_SURFACE_TRIANGLE) makeTriangle(hs, surf, &hp->A[s], &hp->E1[s], &hp->E2[s], &hp->meta[s]);
+            else { hp->A[s] = hp->E1[s] = hp->E2[s] = float4{0, 0, 0, 0}; hp->meta[s] = TriMeta{0, surf}; }
         }
     });
     lap("pack primitives");
-    r.n_spheres = (uint32_t)r.h_spheres.size();
-    r.n_list = 0;
-    r.root = r.info.root;
-    r.mode = MODE_BVH;
+    h->root = h->info.root;
+    h->mode = MODE_BVH;
+    return h;
+}
+
+static int uploadRep(zrt_scene *sc, DevRep &r) {
+    const HostRep &h = *r.host;
+    if (h.mode == MODE_BVH && h.info.max_depth + 2 >= (uint32_t)TRAVERSAL_STACK)
+        return fail(ZRT_ERR_INVALID, "BVH deeper than the traversal stack; drop ZRT_FLAG_BVH_REFERENCE");
+    BuildLap lap;
     cudaStream_t st = sc->stream;
-    CUDA_TRY(r.spheres.upload(r.h_spheres, st));
-    CUDA_TRY(r.triA.upload(A, st)); CUDA_TRY(r.triE1.upload(E1, st)); CUDA_TRY(r.triE2.upload(E2, st));
-    CUDA_TRY(r.triMeta.upload(meta, st));
-    CUDA_TRY(r.nodes.upload(r.info.nodes.data(), r.info.nodes.size(), st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(r.spheres.upload(h.spheres, st));
+    CUDA_TRY(r.list.upload(h.list, st));
+    CUDA_TRY(r.triA.upload(h.A.data(), h.A.size(), st));
+    CUDA_TRY(r.triE1.upload(h.E1.data(), h.E1.size(), st));
+    CUDA_TRY(r.triE2.upload(h.E2.data(), h.E2.size(), st));
+    CUDA_TRY(r.triMeta.upload(h.meta.data(), h.meta.size(), st));
+    CUDA_TRY(r.nodes.upload(h.info.nodes.data(), h.info.nodes.size(), st));
+    CUDA_TRY(cudaStreamSynchronize(st)); // visible to every stream; the host arrays may go away
     lap("upload");
+    r.mode = h.mode;
+    r.n_spheres = (uint32_t)h.spheres.size();
+    r.n_list = h.n_list;
+    r.root = h.root;
     r.ready = true;
     return ZRT_OK;
 }
 
-// raytrace.zig:111-133 preprocessSufraces: BVH iff flag and more than 10 surfaces
-int selectRep(zrt_scene *sc, const zrt_params *p, DevRep **out) {
+DevRep *repFor(zrt_scene *sc, const zrt_params *p) {
     const bool use_bvh = p->bounded_volume_hierarchy != 0 && sc->host.surfaces.size() > 10;
-    DevRep *r = !use_bvh ? &sc->rep_list : ((p->flags & ZRT_FLAG_BVH_REFERENCE) ? &sc->rep_bvh : &sc->rep_sah);
+    return !use_bvh ? &sc->rep_list : ((p->flags & ZRT_FLAG_BVH_REFERENCE) ? &sc->rep_bvh : &sc->rep_sah);
+}
+
+// raytrace.zig:111-133 preprocessSufraces: BVH iff flag and more than 10 surfaces.  A representation whose host half
+// was flattened elsewhere (r->host set by zrt_multi: one flattening for all replicas) is only uploaded here.
+int selectRep(zrt_scene *sc, const zrt_params *p, DevRep **out) {
+    DevRep *r = repFor(sc, p);
     if (!r->ready) {
         const auto t0 = std::chrono::steady_clock::now();
         int rc;
         try { // nothing may throw across the C ABI
-            rc = !use_bvh ? buildListRep(sc, *r) : buildBvhRep(sc, *r, r == &sc->rep_sah);
+            if (!r->host) r->host = (r == &sc->rep_list) ? flattenList(sc->host, sc->all_spheres) : flattenBvh(sc->host, r == &sc->rep_sah);
+            rc = uploadRep(sc, *r);
         } catch (const std::bad_alloc &) {
             return fail(ZRT_ERR_OOM, "out of host memory while flattening the scene");
         } catch (const std::exception &e) {
@@ -345,13 +273,6 @@ int selectRep(zrt_scene *sc, const zrt_params *p, DevRep **out) {
     *out = r;
     return ZRT_OK;
 }
-
-struct Plan {
-    KParams P;
-    int mode;
-    uint32_t n_samples;
-    size_t n_floats;
-};
 
 int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *r, Plan *plan) {
     if (!cam || !p) return fail(ZRT_ERR_INVALID, "camera/params is NULL");
@@ -383,13 +304,24 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     // 500^2 and below -> 32.  BVH / surface-list scenes: 32, i.e. the 32 lanes of a warp trace 32 slices of ONE pixel,
     // so their primary rays walk the same nodes (measured against 8: C2 13.2 -> 11.0 ms, C3 36.0 -> 34.2, C4 119 -> 101).
     // The caller can pin it (sample_chunks = 1 reproduces the reference's sequential f32 sum per pixel).
+    // k_trace_pool (K1q) holds 4 x P.pool items per block instead of 128: the same rule over its slot count.
+    // the slot word of k_trace_pool packs the sample index in 17 bits, the bounce count in 8, pixel coordinates in 16 each
+    const bool ext = (p->flags & (ZRT_FLAG_SAMPLER_HALTON | ZRT_FLAG_RUSSIAN_ROULETTE)) != 0;
+    const bool pool_ok = r->mode == MODE_SPHERES && p->max_depth < 255u && p->samples_per_pixel < 65536u &&
+                         p->width < 65536u && p->height < 65536u && !ext && !(p->flags & ZRT_FLAG_KERNEL_SORTED);
+    uint32_t pool = 0;
+    if ((p->flags & ZRT_FLAG_KERNEL_POOL) && !(p->flags & ZRT_FLAG_KERNEL_THREAD) && pool_ok) {
+        pool = 128;
+        if (const char *e = std::getenv("ZRT_POOL_SLOTS")) pool = (uint32_t)std::atoi(e) >= 128u ? 128u : 64u;
+    }
     uint32_t lanes = p->sample_chunks;
     if (lanes == 0) {
         lanes = 32u;
         if (r->mode == MODE_SPHERES) {
             static int sms = 0;
             if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device) != cudaSuccess) sms = 148;
-            const double target = 54.0 * 1024.0 * (double)sms / (double)(pixels ? pixels : 1); // 8 blocks x 128 lanes per SM
+            const double resident = pool == 128 ? 7.0 * 512.0 : (pool == 64 ? 8.0 * 256.0 : 8.0 * 128.0); // items per SM
+            const double target = 54.0 * resident * (double)sms / (double)(pixels ? pixels : 1);
             lanes = 1u;
             while (lanes < 32u && (double)lanes * 1.41421356 < target) lanes <<= 1; // nearest power of two
         }
@@ -417,7 +349,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         for (uint32_t i = 0; i < MAX_INLINE_SPHERES; i++) {
             KParams::SpherePair &pr = P.inl[i / 2];
             if (i < r->n_spheres) {
-                const DevSphere &sp = r->h_spheres[i];
+                const DevSphere &sp = r->host->spheres[i];
                 pr.ncx[i & 1] = -sp.cx; pr.ncy[i & 1] = -sp.cy; pr.ncz[i & 1] = -sp.cz; pr.nr2[i & 1] = -sp.r2;
             } else {
                 pr.ncx[i & 1] = pr.ncy[i & 1] = pr.ncz[i & 1] = 0.0f;
@@ -465,7 +397,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.pk_rcp[0] = P.rcp_width; P.pk_rcp[1] = P.rcp_height;
     if (r->mode == MODE_SPHERES)
         for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++) {
-            const DevSphere &sp = r->h_spheres[i];
+            const DevSphere &sp = r->host->spheres[i];
             KParams::SphereX2 &e = P.inl2[i];
             e.ncx[0] = e.ncx[1] = -sp.cx; e.ncy[0] = e.ncy[1] = -sp.cy; e.ncz[0] = e.ncz[1] = -sp.cz;
             e.nr2[0] = e.nr2[1] = -sp.r2;
@@ -474,13 +406,16 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.inl_kinds = 0;
     if (r->mode == MODE_SPHERES)
         for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++)
-            P.inl_kinds |= ((r->h_spheres[i].material >> MAT_KIND_SHIFT) & 3u) << (2u * i);
-    const bool pool_ok = r->mode == MODE_SPHERES && p->max_depth < 65535u && p->width < 65536u && p->height < 65536u &&
-                         !P.halton && !P.roulette && !P.sorted_shading;
-    if ((p->flags & ZRT_FLAG_KERNEL_POOL) && !(p->flags & ZRT_FLAG_KERNEL_THREAD) && pool_ok) {
-        P.pool = 64;
-        if (const char *e = std::getenv("ZRT_POOL_SLOTS")) P.pool = (uint32_t)std::atoi(e) >= 128u ? 128u : 64u;
-    }
+            P.inl_kinds |= ((r->host->spheres[i].material >> MAT_KIND_SHIFT) & 3u) << (2u * i);
+    if (r->mode == MODE_SPHERES)
+        for (uint32_t i = 0; i < MAX_INLINE_SPHERES; i++) { // the operations of closest_spheres_inline, once, on the host
+            const KParams::SpherePair &s = P.inl[i / 2];
+            const float ocx = P.ox + s.ncx[i & 1], ocy = P.oy + s.ncy[i & 1], ocz = P.oz + s.ncz[i & 1];
+            const float c = ((ocx * ocx + ocy * ocy) + ocz * ocz) + s.nr2[i & 1];
+            KParams::SpherePair &q = P.inl_prim[i / 2];
+            q.ncx[i & 1] = ocx; q.ncy[i & 1] = ocy; q.ncz[i & 1] = ocz; q.nr2[i & 1] = -c;
+        }
+    P.pool = pool;
     P.two_paths = (r->mode == MODE_SPHERES && (p->flags & ZRT_FLAG_KERNEL_X2) && !P.sorted_shading && !P.halton && !P.roulette && !P.pool) ? 1u : 0u;
     plan->mode = r->mode;
     plan->n_floats = (size_t)p->width * p->height * 3;
@@ -501,7 +436,7 @@ cudaError_t orderAfterUser(zrt_scene *sc, cudaStream_t st) {
 
 // enqueue everything for one render on `st`; d_rgb receives the final image
 int enqueueRender(zrt_scene *sc, Plan &plan, float *d_rgb, unsigned long long *d_counters, cudaStream_t st,
-                  cudaEvent_t e_k0, cudaEvent_t e_k1, cudaEvent_t e_r1, uint32_t *launches, uint8_t *d_rgb8 = nullptr) {
+                  cudaEvent_t e_k0, cudaEvent_t e_k1, cudaEvent_t e_r1, uint32_t *launches, uint8_t *d_rgb8) {
     KParams &P = plan.P;
     if ((P.lanes > 1 && plan.n_floats * P.lanes > sc->part.n) || sc->work.n < 1) quiesce(sc); // about to reallocate scratch
     CUDA_TRY(orderAfterUser(sc, st));
@@ -555,7 +490,7 @@ int requireDevice(zrt_scene *sc) {
     return ZRT_OK;
 }
 
-} // namespace
+} // namespace zrt
 
 extern "C" {
 
@@ -704,7 +639,7 @@ static int renderToHost(zrt_scene *sc, const zrt_camera *camera, const zrt_param
         timing->resolve_ms = r;
         timing->total_ms = tot;
         timing->launches = launches;
-        timing->bvh_nodes = (uint32_t)rep->info.nodes.size();
+        timing->bvh_nodes = (uint32_t)rep->host->info.nodes.size();
     }
     return ZRT_OK;
 }
@@ -777,7 +712,7 @@ int zrt_primary_hits(zrt_scene *sc, const zrt_camera *camera, const zrt_params *
 static const FlatBvh *hostBvh(zrt_scene *sc, uint32_t flags) {
     const int k = (flags & ZRT_FLAG_BVH_REFERENCE) ? 0 : 1;
     DevRep &r = k ? sc->rep_sah : sc->rep_bvh;
-    if (r.ready) return &r.info;
+    if (r.host) return &r.host->info;
     if (!sc->host_bvh_ready[k]) {
         try {
             build_flat_bvh(sc->host, k != 0, &sc->host_bvh[k]);

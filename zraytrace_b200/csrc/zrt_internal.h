@@ -147,6 +147,7 @@ struct KParams {
     uint32_t two_paths; // 1: k_trace_x2
     uint32_t pool;      // spheres-only scenes: slots per warp of k_trace_pool (0 = k_trace)
     uint32_t inl_kinds; // ZRT_MATERIAL_* of inline sphere i in bits 2i, 2i+1
+    SpherePair inl_prim[MAX_INLINE_SPHERES / 2]; // rays from the camera origin: (oc.x, oc.y, oc.z, -(|oc|^2 - r^2)) per sphere
 };
 
 enum TraceMode { MODE_SPHERES = 0, MODE_LIST = 1, MODE_BVH = 2 };

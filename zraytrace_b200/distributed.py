@@ -45,6 +45,23 @@ def reduce_and_scale(accum, counters, samples_per_pixel, group=None, dst=0):
     return is_dst
 
 
+def create_group(built_scene, device, group=None):
+    """One process per GPU (torchrun): every rank of the torch.distributed group gets the same NCCL id - made by
+    libzrt on rank 0, broadcast as 128 bytes through torch.distributed - and joins libzrt's OWN communicator
+    (zrt_multi_create_rank).  From then on the per-step path is libzrt only: render, ncclReduce, 1/spp, copy home."""
+    import torch
+    import torch.distributed as dist
+
+    from . import lib as Z
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return Z.MultiScene(built_scene, devices=[device])
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ids = [Z.comm_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0, group=group)
+    return Z.MultiScene(built_scene, device=device, comm_id=ids[0], rank=rank, world=world)
+
+
 def render_distributed(dev_scene, camera, params, accum=None, counters=None, group=None):
     """Render this rank's share on its GPU and reduce to rank 0.
 

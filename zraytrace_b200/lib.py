@@ -43,6 +43,18 @@ def lib():
         L.zrt_scene_launch_count.argtypes = [C.c_void_p]
         L.zrt_scene_launch_count.restype = C.c_uint64
         L.zrt_build_features.restype = C.c_uint32
+        L.zrt_comm_id.argtypes = [C.c_void_p]
+        L.zrt_multi_create.argtypes = [P(A.SceneDesc), P(C.c_int), C.c_int, P(C.c_void_p)]
+        L.zrt_multi_create_rank.argtypes = [P(A.SceneDesc), C.c_int, C.c_void_p, C.c_int, C.c_int, P(C.c_void_p)]
+        L.zrt_multi_destroy.argtypes = [C.c_void_p]
+        L.zrt_multi_reload.argtypes = [C.c_void_p, P(A.SceneDesc)]
+        L.zrt_multi_destroy.restype = None
+        L.zrt_multi_render.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), C.c_void_p, P(A.Counters), P(A.Timing)]
+        L.zrt_multi_world_size.argtypes = [C.c_void_p]
+        L.zrt_multi_launch_count.argtypes = [C.c_void_p]
+        L.zrt_multi_launch_count.restype = C.c_uint64
+        L.zrt_multi_image_device.argtypes = [C.c_void_p]
+        L.zrt_multi_image_device.restype = C.c_void_p
         L.zrt_trace_statistics.argtypes = [C.c_void_p, P(A.Camera), P(A.Params), P(A.TraceStats)]
         L.zrt_selftest.argtypes = [C.c_int, P(C.c_uint64)]
         L.zrt_measure_peaks.argtypes = [C.c_int, P(C.c_double), C.c_int]
@@ -178,6 +190,74 @@ class Scene:
         vis = np.zeros(self.n_surfaces, np.uint8)
         _check(lib().zrt_scene_bvh_order(self._h, order.ctypes.data, vis.ctypes.data))
         return order, vis.astype(bool)
+
+
+def comm_id():
+    """128 opaque bytes (an ncclUniqueId) that every process of a one-process-per-GPU group must be given."""
+    buf = (C.c_uint8 * A.ZRT_COMM_ID_BYTES)()
+    _check(lib().zrt_comm_id(buf))
+    return bytes(buf)
+
+
+def nccl_version():
+    return int(lib().zrt_nccl_version())
+
+
+class MultiScene:
+    """`zrt_multi*`: the scene replicated on several GPUs, samples-per-pixel split across them, ONE NCCL reduce of the
+    f32 accumulators to rank 0 (include/zrt.h "multi-GPU").
+
+    MultiScene(scene, devices=[0, 1, ...])                      one process drives all devices
+    MultiScene(scene, device=d, comm_id=id, rank=r, world=w)    one process per device (torchrun / MPI)"""
+
+    def __init__(self, built_scene_or_desc, devices=None, device=None, comm_id=None, rank=0, world=1):
+        desc = getattr(built_scene_or_desc, "desc", built_scene_or_desc)
+        self._h = C.c_void_p()
+        if device is None:
+            devs = list(devices) if devices is not None else [0]
+            arr = (C.c_int * len(devs))(*devs)
+            _check(lib().zrt_multi_create(C.byref(desc), arr, len(devs), C.byref(self._h)))
+            self.rank, self.world = 0, len(devs)
+        else:
+            idbuf = (C.c_uint8 * A.ZRT_COMM_ID_BYTES)(*(comm_id or bytes(A.ZRT_COMM_ID_BYTES)))
+            _check(lib().zrt_multi_create_rank(C.byref(desc), device, idbuf, rank, world, C.byref(self._h)))
+            self.rank, self.world = rank, world
+
+    def close(self):
+        if self._h:
+            lib().zrt_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def render(self, camera, params, out=None, to_host=True):
+        """-> (image float32 [H][W][3] or None, Counters, Timing).  Image and counters are meaningful on the process
+        that owns rank 0; to_host=False leaves the image on rank 0's device (timing.total_ms is device time)."""
+        img = None
+        if to_host and self.rank == 0:
+            img = _out_buffer(out, (params.height, params.width, 3), np.float32)
+        cnt, tm = A.Counters(), A.Timing()
+        _check(lib().zrt_multi_render(self._h, C.byref(camera), C.byref(params), img.ctypes.data if img is not None else None,
+                                      C.byref(cnt), C.byref(tm)))
+        return img, cnt, tm
+
+    def launch_count(self):
+        return int(lib().zrt_multi_launch_count(self._h))
+
+    def reload(self, built_scene_or_desc):
+        """Replace the scene on every local device (flatten + H2D again); the communicator is kept."""
+        desc = getattr(built_scene_or_desc, "desc", built_scene_or_desc)
+        _check(lib().zrt_multi_reload(self._h, C.byref(desc)))
 
 
 def selftest(device=0):
