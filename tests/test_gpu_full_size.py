@@ -61,7 +61,8 @@ def test_full_depth_paths_match_the_oracle_at_the_configuration_camera(workload)
     p = A.make_params(w, h, 16, wl["depth"], x_limit=wl.get("x_limit", A.ZRT_XLIMIT_HEIGHT), seed=42, sample_chunks=1)
     img_o, c_o, st = zro_py.render(hs, hs.camera, p, rng=zro_py.RNG_CTR, math=zro_py.MATH_SPEC,
                                    traversal=zro_py.TRAVERSAL_TIGHT, threads=os.cpu_count() or 1)
-    for flags in (0, A.ZRT_FLAG_KERNEL_THREAD, A.ZRT_FLAG_KERNEL_WARP, A.ZRT_FLAG_BVH_REFERENCE):
+    for flags in (0, A.ZRT_FLAG_KERNEL_THREAD, A.ZRT_FLAG_KERNEL_WARP, A.ZRT_FLAG_KERNEL_POOL, A.ZRT_FLAG_BVH_REFERENCE,
+                  A.ZRT_FLAG_KERNEL_POOL | A.ZRT_FLAG_BVH_REFERENCE):
         p.flags = flags
         img_g, c_g, _ = dev.render(hs.camera, p)
         assert c_g.as_dict() == c_o.as_dict(), (name, flags, c_g.as_dict(), c_o.as_dict())

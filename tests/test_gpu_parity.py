@@ -180,6 +180,22 @@ def test_two_paths_per_thread_kernel(built, w, h, spp, depth, chunks):
     np.testing.assert_allclose(img_x, img_o, rtol=2e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name,w,spp,depth", [("three_balls", 96, 16, 30), ("teapot", 96, 16, 30), ("bunny_glass", 80, 12, 30),
+                                               ("teapot_circle", 64, 8, 20), ("man", 64, 40, 5)])
+def test_pool_kernels_every_slot_count(built, name, w, spp, depth, monkeypatch):
+    """k_trace_pool (sphere scenes) / k_trace_bpool (BVH scenes) at every pool size the library instantiates, automatic
+    and pinned slice counts: the paths, counters and image bits of the thread kernel."""
+    sc, cam, dev = built(name)
+    for chunks in (0, 1, 4):
+        img_t, c_t, _ = dev.render(cam, A.make_params(w, w, spp, depth, sample_chunks=chunks, flags=A.ZRT_FLAG_KERNEL_THREAD))
+        for slots in ("64", "96", "128"):
+            monkeypatch.setenv("ZRT_POOL_SLOTS", slots)
+            img_p, c_p, _ = dev.render(cam, A.make_params(w, w, spp, depth, sample_chunks=chunks, flags=A.ZRT_FLAG_KERNEL_POOL))
+            _counters_equal(c_t, c_p)
+            assert np.array_equal(img_t.view(np.uint32), img_p.view(np.uint32)), (name, chunks, slots)
+    monkeypatch.delenv("ZRT_POOL_SLOTS")
+
+
 def test_reference_topology_full_paths(built):
     sc, cam, dev = built("teapot")
     p = A.make_params(64, 64, 8, 30, sample_chunks=1)

@@ -307,12 +307,15 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     // k_trace_pool (K1q) holds 4 x P.pool items per block instead of 128: the same rule over its slot count.
     // the slot word of k_trace_pool packs the sample index in 17 bits, the bounce count in 8, pixel coordinates in 16 each
     const bool ext = (p->flags & (ZRT_FLAG_SAMPLER_HALTON | ZRT_FLAG_RUSSIAN_ROULETTE)) != 0;
-    const bool pool_ok = r->mode == MODE_SPHERES && p->max_depth < 255u && p->samples_per_pixel < 65536u &&
+    const bool pool_ok = (r->mode == MODE_SPHERES || r->mode == MODE_BVH) && p->max_depth < 255u && p->samples_per_pixel < 65536u &&
                          p->width < 65536u && p->height < 65536u && !ext && !(p->flags & ZRT_FLAG_KERNEL_SORTED);
     uint32_t pool = 0;
     if ((p->flags & ZRT_FLAG_KERNEL_POOL) && !(p->flags & ZRT_FLAG_KERNEL_THREAD) && pool_ok) {
         pool = 128;
-        if (const char *e = std::getenv("ZRT_POOL_SLOTS")) pool = (uint32_t)std::atoi(e) >= 128u ? 128u : 64u;
+        if (const char *e = std::getenv("ZRT_POOL_SLOTS")) {
+            const uint32_t v = (uint32_t)std::atoi(e);
+            pool = v >= 128u ? 128u : ((v >= 96u && r->mode == MODE_BVH) ? 96u : 64u);
+        }
     }
     uint32_t lanes = p->sample_chunks;
     if (lanes == 0) {
@@ -386,6 +389,14 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     if (const char *e = std::getenv("ZRT_WS_THRESHOLDS")) { // "node,leaf,shade": tuning sweeps (tools/ws_sweep.sh)
         unsigned a = 0, b = 0, c = 0;
         if (std::sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { P.ws_node_min = a; P.ws_leaf_min = b; P.ws_shade_min = c; }
+    }
+    if (pool && r->mode == MODE_BVH) { // k_trace_bpool (K1p): node steps at >= 12 lanes, leaves at >= 2, refill at >= 8 idle, dry batch >= 16
+        P.ws_node_min = 12; P.ws_leaf_min = 2; P.ws_shade_min = 8; P.ws_batch_min = 16;
+        if (const char *e = std::getenv("ZRT_POOL_THRESHOLDS")) { // "node,leaf,idle,batch": tuning sweeps
+            unsigned a = 0, b = 0, c = 0, d = 0;
+            if (std::sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4 && c >= 1 && c <= 32) { P.ws_node_min = a; P.ws_leaf_min = b; P.ws_shade_min = c; P.ws_batch_min = d; }
+        }
+        P.warp_scheduled = 0;
     }
     P.halton = (p->flags & ZRT_FLAG_SAMPLER_HALTON) ? 1u : 0u;
     P.roulette = (p->flags & ZRT_FLAG_RUSSIAN_ROULETTE) ? 1u : 0u;
