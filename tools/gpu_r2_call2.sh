@@ -12,6 +12,7 @@ print('$1 $2 chunks=$3 $4', [round(x['kernel_ms'],3) for x in r], r[-1]['rays_pr
 {
 ab c5 thread 0 X=1
 ab c5 pool 0 ZRT_POOL_SLOTS=128
+ab c5 pool 0 ZRT_POOL_SPLIT=0
 for c in 8 16 32; do ab c5 pool $c ZRT_POOL_SLOTS=64; ab c5 pool $c ZRT_POOL_SLOTS=128; done
 for w in c2 c3 c4; do
   ab $w thread 0 X=1; ab $w warp 0 X=1

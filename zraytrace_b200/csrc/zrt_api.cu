@@ -415,9 +415,15 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         }
     // k_trace_pool (K1q): spheres-only scenes, bounce count and pixel coordinates packed in 16 bits each
     P.inl_kinds = 0;
+    P.pool_split = 1;
+    if (const char *e = std::getenv("ZRT_POOL_SPLIT")) P.pool_split = std::atoi(e) ? 1u : 0u; // A/B hook
     if (r->mode == MODE_SPHERES)
-        for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++)
-            P.inl_kinds |= ((r->host->spheres[i].material >> MAT_KIND_SHIFT) & 3u) << (2u * i);
+        for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++) { // PoolKind: 1 + kind, image variants at 4, 5
+            const uint32_t mat = r->host->spheres[i].material, kind = (mat >> MAT_KIND_SHIFT) & 3u;
+            uint32_t ring = 1u + kind;
+            if (P.pool_split && (mat & MAT_IMAGE_BIT) && kind != ZRT_MATERIAL_DIELECTRIC) ring = 4u + kind;
+            P.inl_kinds |= ring << (3u * i);
+        }
     if (r->mode == MODE_SPHERES)
         for (uint32_t i = 0; i < MAX_INLINE_SPHERES; i++) { // the operations of closest_spheres_inline, once, on the host
             const KParams::SpherePair &s = P.inl[i / 2];
