@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
                     slot = S.ring[BP_TRAV_RING][(trav_head + rank) & RM];
                     o = mk(S.ox[slot], S.oy[slot], S.oz[slot]);
                     d = mk(S.dx[slot], S.dy[slot], S.dz[slot]);
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(d.x));
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(d.y));
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.z) : "f"(d.z));
+                    inv.x = rcp_approx(d.x);
+                    inv.y = rcp_approx(d.y);
+                    inv.z = rcp_approx(d.z);
                     h.t = F_INF; h.ref = REF_EMPTY; h.slot = 0xFFFFFFFFu; h.u = h.v = 0.0f;
                     sp = 0;
                     cur = P.root;
