@@ -48,6 +48,7 @@ namespace zrt_emu {
 enum Tag : int { T_NONE, T_BALLOT, T_ANY, T_SHFL, T_MATCH, T_REDADD, T_SYNC };
 struct Warp {
     uint32_t arrived = 0, gen = 0, exited = 0;
+    unsigned long long seen[64] = {};
     int tag = T_NONE;
     uint32_t vals[32], aux[32], res[32];
     uint32_t res_scalar = 0;
@@ -61,6 +62,7 @@ struct Fiber {
     bool done = false;
     uint32_t wait_gen = 0;
     bool waiting = false;
+    unsigned long long tick = 0; // ZRT_PROF_TICK: the lane's iteration of the kernel's main loop (loops are warp-uniform)
 };
 struct Machine {
     ucontext_t main_ctx;
@@ -158,6 +160,22 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()> &b
     m.body = nullptr;
 }
 } // namespace zrt_emu
+
+// ---- section profile: how often a warp ran a code region and with how many lanes (ZRT_PROF in the kernels) ----
+namespace zrt_emu {
+struct Prof { unsigned long long calls[64], lanes[64]; };
+inline Prof g_prof{};
+inline void prof(int sec, bool on) {
+    if (!on) return;
+    Fiber &f = *M().cur;
+    Warp &w = *f.warp;
+    if (w.seen[sec] != f.tick) { w.seen[sec] = f.tick; g_prof.calls[sec]++; }
+    g_prof.lanes[sec]++;
+}
+inline void prof_tick() { M().cur->tick++; }
+} // namespace zrt_emu
+#define ZRT_PROF(sec, on) zrt_emu::prof((sec), (on))
+#define ZRT_PROF_TICK() zrt_emu::prof_tick()
 
 #define threadIdx (zrt_emu::M().cur->tid)
 #define blockIdx (zrt_emu::M().cur->bid)

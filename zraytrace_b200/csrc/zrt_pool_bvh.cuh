@@ -96,35 +96,50 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
     h.t = F_INF; h.ref = REF_EMPTY; h.slot = 0xFFFFFFFFu; h.u = h.v = 0.0f;
     uint2 stack[TRAVERSAL_STACK]; // (ref, entry distance of the subtree)
 
+    uint32_t burst_floor = 33u; // node steps run back to back while at least this many lanes are at an inner node (33: decide anew)
     for (;;) {
-        // ---- scheduler (warp-uniform).  Fast path: nearly every lane is at an inner node ----
+        // ---- scheduler (warp-uniform).  A decision for N holds for a burst: the warp keeps stepping nodes on ONE ballot per
+        //      step until a quarter of the lanes that started the burst have left the inner nodes; every other section
+        //      is followed by a full decision ----
+        ZRT_PROF_TICK();
+        ZRT_PROF(0, true);
         const uint32_t n_node = __popc(__ballot_sync(0xffffffffu, st == BS_NODE));
         int section = 0; // 0 = N, 1 = L, 2 = X, 3 = S
         uint32_t k = 0;  // S: the kind to shade
-        if (n_node + P.ws_shade_min <= 32u) {
+        if (n_node < burst_floor) {
+            ZRT_PROF(1, true);
+            burst_floor = 33u;
             const uint32_t n_leaf = __popc(__ballot_sync(0xffffffffu, st == BS_LEAF));
             const uint32_t n_done = __popc(__ballot_sync(0xffffffffu, st == BS_DONE));
             const uint32_t n_idle = 32u - n_node - n_leaf; // done + free
-            const uint32_t c0 = counts & 0xFFu, c1 = (counts >> 8) & 0xFFu, c2 = (counts >> 16) & 0xFFu, c3 = counts >> 24;
-            const uint32_t m01 = max(c0, c1), m23 = max(c2, c3), best = max(m01, m23);
-            k = (m01 >= m23) ? ((c0 >= c1) ? 0u : 1u) : ((c2 >= c3) ? 2u : 3u);
             const bool x_useful = n_done > 0u || (trav_count > 0u && n_idle > 0u);
             const bool hungry = n_idle >= P.ws_shade_min; // enough lanes without a query to make a refill worth a section
+            const bool full_batch = (counts & 0xE0E0E0E0u) != 0u; // some shade ring holds >= 32 slots
             if (hungry && x_useful) section = 2;
-            else if (best >= 32u || (hungry && best >= P.ws_batch_min)) section = 3; // a full batch, or TRAV ran dry
+            else if (full_batch || (hungry && counts != 0u)) section = 3; // a full batch, or TRAV ran dry (batch size checked below)
             else if (n_node >= P.ws_node_min) section = 0;
             else if (n_leaf >= P.ws_leaf_min) section = 1;
-            else { // nothing runs well: take what occupies the most lanes
-                const uint32_t x_use = x_useful ? max(n_done, min(n_idle, trav_count)) : 0u;
-                const uint32_t top = max(max(n_node, n_leaf), max(x_use, best));
-                if (top == 0u) break; // all rings empty, every lane free: the queue is exhausted and all paths ended
-                section = (top == best) ? 3 : ((top == n_node) ? 0 : ((top == n_leaf) ? 1 : 2));
+            else section = 4; // nothing runs well: take what occupies the most lanes
+            if (section >= 3) {
+                const uint32_t c0 = counts & 0xFFu, c1 = (counts >> 8) & 0xFFu, c2 = (counts >> 16) & 0xFFu, c3 = counts >> 24;
+                const uint32_t m01 = max(c0, c1), m23 = max(c2, c3), best = max(m01, m23);
+                k = (m01 >= m23) ? ((c0 >= c1) ? 0u : 1u) : ((c2 >= c3) ? 2u : 3u);
+                if (section == 3 && best < 32u && best < P.ws_batch_min) // dry, but the fullest batch is too small to be worth it
+                    section = (n_node >= P.ws_node_min) ? 0 : ((n_leaf >= P.ws_leaf_min) ? 1 : 4);
+                if (section == 4) {
+                    const uint32_t x_use = x_useful ? max(n_done, min(n_idle, trav_count)) : 0u;
+                    const uint32_t top = max(max(n_node, n_leaf), max(x_use, best));
+                    if (top == 0u) break; // all rings empty, every lane free: the queue is exhausted and all paths ended
+                    section = (top == best) ? 3 : ((top == n_node) ? 0 : ((top == n_leaf) ? 1 : 2));
+                }
             }
+            if (section == 0) burst_floor = max(min(P.ws_node_min, n_node), (n_node * 3u) >> 2);
         }
 
         bool need_pop = false;
         if (section == 0) {
             // ================= N: one node step (bvh.zig:187-205 as an ordered stack traversal, see closest_bvh) =================
+            ZRT_PROF(2, st == BS_NODE);
             if (st == BS_NODE) {
                 const float4 *q = reinterpret_cast<const float4 *>(P.nodes + cur);
                 const float4 q0 = ldg4(q), q1 = ldg4(q + 1), q2 = ldg4(q + 2);
@@ -146,6 +161,7 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
             }
         } else if (section == 1) {
             // ================= L: one postponed leaf test (sphere.zig:31-71 / triangle.zig:48-70) =================
+            ZRT_PROF(3, st == BS_LEAF);
             if (st == BS_LEAF) {
                 leaf_test<false>(P, cur, o, d, h);
                 need_pop = true;
@@ -153,6 +169,8 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
         } else if (section == 2) {
             // ================= X: hand finished queries over, re-arm free lanes =================
             uint32_t nk = PK_IDLE;
+            ZRT_PROF(13, true);
+            ZRT_PROF(4, st == BS_DONE);
             if (st == BS_DONE) {
                 if (h.ref == REF_EMPTY) { // raytrace.zig:82-86: the path ends on the background
                     S.meta[slot] |= PM_BG;
@@ -183,6 +201,7 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
                 const uint32_t want = __ballot_sync(0xffffffffu, st == BS_FREE);
                 const uint32_t cnt = min((uint32_t)__popc(want), trav_count);
                 const uint32_t rank = __popc(want & lane_lt);
+                ZRT_PROF(5, st == BS_FREE && rank < cnt);
                 if (st == BS_FREE && rank < cnt) {
                     slot = S.ring[BP_TRAV_RING][(trav_head + rank) & RM];
                     o = mk(S.ox[slot], S.oy[slot], S.oz[slot]);
@@ -204,6 +223,7 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
             const uint32_t cnt_k = (counts >> (8 * k)) & 0xFFu;
             const uint32_t m = min(cnt_k, 32u);
             const bool active = lane < m;
+            ZRT_PROF(6 + (int)k, active);
             const uint32_t head = (heads >> (8 * k)) & 0xFFu;
             const uint32_t ss = S.ring[k][(head + lane) & RM];
             heads = (heads & ~(0xFFu << (8 * k))) | (((head + m) & RM) << (8 * k));
@@ -315,6 +335,7 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
             }
             __syncwarp(); // slot state and ring entries written by one lane are read by another in a later section
         }
+        ZRT_PROF(12, need_pop);
         if (need_pop) { // skip subtrees that fell behind the closest hit found since they were pushed
             st = BS_DONE;
             while (sp > 0) {
