@@ -391,10 +391,12 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         if (std::sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { P.ws_node_min = a; P.ws_leaf_min = b; P.ws_shade_min = c; }
     }
     if (pool && r->mode == MODE_BVH) { // k_trace_bpool (K1p): node steps at >= 12 lanes, leaves at >= 2, refill at >= 8 idle, dry batch >= 16
-        P.ws_node_min = 12; P.ws_leaf_min = 2; P.ws_shade_min = 8; P.ws_batch_min = 16;
-        if (const char *e = std::getenv("ZRT_POOL_THRESHOLDS")) { // "node,leaf,idle,batch": tuning sweeps
-            unsigned a = 0, b = 0, c = 0, d = 0;
-            if (std::sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4 && c >= 1 && c <= 32) { P.ws_node_min = a; P.ws_leaf_min = b; P.ws_shade_min = c; P.ws_batch_min = d; }
+        P.ws_node_min = 12; P.ws_leaf_min = 2; P.ws_shade_min = 8; P.ws_batch_min = 16; P.ws_burst_num = 3;
+        if (const char *e = std::getenv("ZRT_POOL_THRESHOLDS")) { // "node,leaf,idle,batch[,burst]": tuning sweeps
+            unsigned a = 0, b = 0, c = 0, d = 0, f = 3;
+            if (std::sscanf(e, "%u,%u,%u,%u,%u", &a, &b, &c, &d, &f) >= 4 && c >= 1 && c <= 32 && f <= 4) {
+                P.ws_node_min = a; P.ws_leaf_min = b; P.ws_shade_min = c; P.ws_batch_min = d; P.ws_burst_num = f;
+            }
         }
         P.warp_scheduled = 0;
     }

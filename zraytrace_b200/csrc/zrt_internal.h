@@ -115,6 +115,7 @@ struct KParams {
     uint32_t halton, roulette; // sampler extensions (ZRT_FLAG_SAMPLER_HALTON, ZRT_FLAG_RUSSIAN_ROULETTE): k_trace<EXT>
     uint32_t warp_scheduled; // BVH scenes: 1: k_trace_ws (warp-scheduled node / leaf / shade sections)
     uint32_t ws_node_min, ws_leaf_min, ws_shade_min; // k_trace_ws: lanes that must wait for a section before the warp runs it
+    uint32_t ws_burst_num; // k_trace_bpool: a node-step burst ends when fewer than ws_burst_num / 4 of its lanes are left at inner nodes
     uint32_t ws_batch_min; // k_trace_bpool: smallest shade batch worth running when the TRAV ring is dry (ws_shade_min = lanes idle before a refill)
     // scene
     uint32_t n_spheres, n_list;

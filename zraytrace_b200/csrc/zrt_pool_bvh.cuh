@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_bpool(const __grid_consta
                     section = (top == best) ? 3 : ((top == n_node) ? 0 : ((top == n_leaf) ? 1 : 2));
                 }
             }
-            if (section == 0) burst_floor = max(min(P.ws_node_min, n_node), (n_node * 3u) >> 2);
+            if (section == 0) burst_floor = max(min(P.ws_node_min, n_node), (n_node * P.ws_burst_num) >> 2);
         }
 
         bool need_pop = false;
