@@ -254,6 +254,18 @@ inline unsigned __brev(unsigned v) {
     for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
     return r;
 }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) { // PRMT, default mode
+    const unsigned long long xy = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned sel = (s >> (4 * i)) & 0xFu;
+        unsigned b = (unsigned)(xy >> (8 * (sel & 7u))) & 0xFFu;
+        if (sel & 8u) b = (b & 0x80u) ? 0xFFu : 0x00u;
+        r |= b << (8 * i);
+    }
+    return r;
+}
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline float rsqrt_approx(float x) { return (float)(1.0 / std::sqrt((double)x)); }
 inline float rcp_approx(float x) { return (float)(1.0 / (double)x); }

@@ -310,11 +310,16 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     const bool pool_ok = (r->mode == MODE_SPHERES || r->mode == MODE_BVH) && p->max_depth < 255u && p->samples_per_pixel < 65536u &&
                          p->width < 65536u && p->height < 65536u && !ext && !(p->flags & ZRT_FLAG_KERNEL_SORTED);
     uint32_t pool = 0;
-    if ((p->flags & ZRT_FLAG_KERNEL_POOL) && !(p->flags & ZRT_FLAG_KERNEL_THREAD) && pool_ok) {
+    // Sphere-only scenes: launches that are mostly steady state (>= 2^24 samples) run k_trace_pool unless a flag says otherwise
+    // (C5: 35.95 ms against 40.4 ms of k_trace, profiles/r2_a_kernel_ab.log); BVH scenes only on request (k_trace_bpool is
+    // the slower kernel there).
+    const bool pool_auto = r->mode == MODE_SPHERES && !(p->flags & (ZRT_FLAG_KERNEL_X2 | ZRT_FLAG_KERNEL_WARP)) &&
+                           pixels * (uint64_t)plan->n_samples >= (1ull << 24);
+    if (((p->flags & ZRT_FLAG_KERNEL_POOL) || pool_auto) && !(p->flags & ZRT_FLAG_KERNEL_THREAD) && pool_ok) {
         pool = 128;
         if (const char *e = std::getenv("ZRT_POOL_SLOTS")) {
             const uint32_t v = (uint32_t)std::atoi(e);
-            pool = v >= 128u ? 128u : ((v >= 96u && r->mode == MODE_BVH) ? 96u : 64u);
+            pool = v >= 128u ? 128u : (v >= 96u ? 96u : 64u);
         }
     }
     uint32_t lanes = p->sample_chunks;
@@ -417,6 +422,8 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         }
     // k_trace_pool (K1q): spheres-only scenes, bounce count and pixel coordinates packed in 16 bits each
     P.inl_kinds = 0;
+    P.pool_version = 3;
+    if (const char *e = std::getenv("ZRT_POOL_V")) P.pool_version = std::atoi(e) == 2 ? 2u : 3u;
     P.pool_split = 1;
     if (const char *e = std::getenv("ZRT_POOL_SPLIT")) P.pool_split = std::atoi(e) ? 1u : 0u; // A/B hook
     if (r->mode == MODE_SPHERES)
