@@ -136,9 +136,13 @@ enum {
                                    independent uniforms.  Both extensions run on k_trace only and are restated by
                                    the oracle (draw-for-draw parity); zrt_trace_statistics ignores them */
     ZRT_FLAG_KERNEL_X2 = 1u << 7,     /* spheres-only scenes: k_trace_x2, two paths per thread in packed f32x2 (opt-in: ties) */
-    ZRT_FLAG_KERNEL_POOL = 1u << 8,   /* spheres-only scenes: k_trace_pool, every warp keeps a pool of work items in shared
-                                   memory and runs batches of up to 32 paths that need the same thing next (new sample,
-                                   Lambertian, metal, glass); bit-identical output.  Ignored on other scenes */
+    ZRT_FLAG_KERNEL_POOL = 1u << 8,   /* the slot-pool kernels: every warp keeps a pool of work items in shared memory and runs
+                                   batches of up to 32 paths that need the same thing next (new sample, Lambertian, metal,
+                                   glass, image-textured variants); bit-identical output.  Sphere-only scenes: k_trace_pool3,
+                                   which is also what launches of >= 2^24 samples run without any flag (36 ms against
+                                   40.4 ms of k_trace on the README headline).  BVH scenes: k_trace_bpool (traversal lanes
+                                   re-armed from a ring), measured SLOWER than k_trace_ws and therefore only on request.
+                                   Ignored on surface-list scenes with triangles */
     ZRT_FLAG_KERNEL_SORTED = 1u << 3  /* the block-sorted-shading kernel k_trace_sorted (shared-memory wavefront
                                    inside a thread block).  Images and counters are bit-identical between the
                                    two kernels, only speed differs; the thread kernel measured faster */
