@@ -307,7 +307,12 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     // k_trace_pool (K1q) holds 4 x P.pool items per block instead of 128: the same rule over its slot count.
     // the slot word of k_trace_pool packs the sample index in 17 bits, the bounce count in 8, pixel coordinates in 16 each
     const bool ext = (p->flags & (ZRT_FLAG_SAMPLER_HALTON | ZRT_FLAG_RUSSIAN_ROULETTE)) != 0;
-    const bool pool_ok = (r->mode == MODE_SPHERES || r->mode == MODE_BVH) && p->max_depth < 255u && p->samples_per_pixel < 65536u &&
+#if defined(ZRT_EXPERIMENTS) || defined(ZRT_EMU)
+    const bool pool_modes = r->mode == MODE_SPHERES || r->mode == MODE_BVH; // k_trace_bpool is an experiment (slower than k_trace_ws)
+#else
+    const bool pool_modes = r->mode == MODE_SPHERES;
+#endif
+    const bool pool_ok = pool_modes && p->max_depth < 255u && p->samples_per_pixel < 65536u &&
                          p->width < 65536u && p->height < 65536u && !ext && !(p->flags & ZRT_FLAG_KERNEL_SORTED);
     uint32_t pool = 0;
     // Sphere-only scenes: launches that are mostly steady state (>= 2^24 samples) run k_trace_pool unless a flag says otherwise
@@ -422,9 +427,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         }
     // k_trace_pool (K1q): spheres-only scenes, bounce count and pixel coordinates packed in 16 bits each
     P.inl_kinds = 0;
-    P.pool_version = 3;
-    if (const char *e = std::getenv("ZRT_POOL_V")) P.pool_version = std::atoi(e) == 2 ? 2u : 3u;
-    P.pool_split = 1;
+    P.pool_split = 0; // C5: 34.34 ms without the image rings, 34.60 ms with them (profiles/r2_c_pool3_ab.log)
     if (const char *e = std::getenv("ZRT_POOL_SPLIT")) P.pool_split = std::atoi(e) ? 1u : 0u; // A/B hook
     if (r->mode == MODE_SPHERES)
         for (uint32_t i = 0; i < r->n_spheres && i < MAX_INLINE_SPHERES; i++) { // PoolKind: 1 + kind, image variants at 4, 5
