@@ -58,7 +58,15 @@ def algorithmic_ops(stats, counters):
 # under a profiler is only ever used for these fields): dram bytes read + written, l1tex / lts bytes, issue-slot
 # utilisation and active lanes per instruction.  Filled from profiles/ by hand after each capture.
 NCU = {
-    "c5": {"traffic": 3894528 + 44411136, "source": "profiles/r1_v10_c5_k_trace.txt (1 GPU, 1000 spp, k_trace<0,7>)"},
+    "c5": {"traffic": 92832000 + 416680192, "issue_active_pct": 81.1, "active_lanes": 27.16,
+           "source": "profiles/r2_c_c5_pool3_summary.txt (1 GPU, k_trace_pool3<7,128,7>, 100 spp launch: the 32 partial-sum slices are the "
+                     "same 384 MB at any sample count)"},
+    "c2": {"traffic": 14648832 + 63718656, "issue_active_pct": 76.9, "active_lanes": 17.59,
+           "source": "profiles/r2_c_c2_warp_summary.txt (k_trace_ws, 64 spp launch)"},
+    "c3": {"traffic": 35642112 + 393396480, "issue_active_pct": 70.2, "active_lanes": 21.82,
+           "source": "profiles/r2_c_c3_warp_summary.txt (k_trace_ws, 32 spp launch)"},
+    "c4": {"traffic": 89412864 + 392858112, "issue_active_pct": 72.5, "active_lanes": 21.11,
+           "source": "profiles/r2_c_c4_warp_summary.txt (k_trace_ws, 16 spp launch)"},
 }
 
 

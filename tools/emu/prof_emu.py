@@ -19,7 +19,7 @@ NAMES = {0: "p.iterations", 1: "p.sched slow path", 2: "p.N node step", 3: "p.L 
          20: "w.iterations", 21: "w.sched slow path", 22: "w.N node step", 23: "w.L leaf test", 24: "w.S sections", 25: "w.S background",
          26: "w.S hit record", 27: "w.S lambertian", 28: "w.S metal", 29: "w.S glass", 30: "w.S image texture", 31: "w.S regenerate",
          32: "w.S unit + bookkeeping", 33: "w.pop",
-         40: "q.iterations", 41: "q.S regen", 42: "q.S lambertian", 43: "q.S metal", 44: "q.S glass", 45: "q.S lamb img", 46: "q.S metal img",
+         40: "q.iterations", 41: "q.S regen", 42: "q.S lambertian", 43: "q.S metal", 44: "q.S glass", 45: "q.S lamb img", 46: "q.S hand-over",
          47: "q.common (unit + spheres)", 48: "q.primary spheres", 49: "q.secondary spheres",
          50: "t.iterations", 51: "t.top block", 52: "t.unit + closest hit", 53: "t.background", 54: "t.draw", 55: "t.regenerate",
          56: "t.hit record", 57: "t.lambertian", 58: "t.metal", 59: "t.glass", 60: "t.image texture"}

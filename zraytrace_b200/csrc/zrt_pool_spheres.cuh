@@ -10,6 +10,10 @@
 //     bytes at constant positions, no run-time kind tests, dead state of other kinds removed;
 //   * ring bytes read with PRMT (__byte_perm), the scheduler takes the first ring that can fill a warp and looks for
 //     the fullest one only when none can.
+//   * an item that has run out of samples does not hand its sum over inside the REGEN batch that notices (a ~90-instruction
+//     path a whole warp would run for typically one lane, 31 samples per item at 32 slices): the slot goes onto a ring of its
+//     own (PK_HAND) and 32 of them hand over, take the next 32 items of the global queue - the 32 slices of one pixel - and
+//     start their first sample together.
 // Arithmetic, RNG keys and per-item summation order are those of K1: images and counters are bit-identical.
 #pragma once
 
@@ -26,7 +30,7 @@ DI uint32_t ring_byte(uint32_t w0, uint32_t w1, uint32_t k) { return __byte_perm
 
 // K1q's state shared by the halves of an iteration (all warp-uniform except the per-lane members)
 struct Pool3Rings {
-    uint32_t h0 = 0, c0 = 0, h1 = 0, c1 = 0; // heads / counts, one byte per ring: rings 0-3 in word 0, 4-5 in word 1
+    uint32_t h0 = 0, c0 = 0, h1 = 0, c1 = 0; // heads / counts, one byte per ring: rings 0-3 in word 0, 4-6 in word 1
     template <uint32_t K>
     DI uint32_t head() const { return ((K < 4u ? h0 : h1) >> (8u * (K & 3u))) & 0xFFu; }
     template <uint32_t K>
@@ -38,17 +42,19 @@ struct Pool3Rings {
     }
     // the first ring that fills a warp; the fullest one when none does.  best = its count (0: every ring is empty)
     DI uint32_t choose(uint32_t &best) const {
-        const uint32_t f0 = c0 & 0xE0E0E0E0u, f1 = c1 & 0x0000E0E0u; // bytes >= 32
+        const uint32_t f0 = c0 & 0xE0E0E0E0u, f1 = c1 & 0x00E0E0E0u; // bytes >= 32
         if (f0 | f1) {
             best = 32u;
             return f0 ? (uint32_t)(__ffs((int)f0) - 1) >> 3 : 4u + ((uint32_t)(__ffs((int)f1) - 1) >> 3);
         }
-        const uint32_t a0 = c0 & 0xFFu, a1 = (c0 >> 8) & 0xFFu, a2 = (c0 >> 16) & 0xFFu, a3 = c0 >> 24, a4 = c1 & 0xFFu, a5 = (c1 >> 8) & 0xFFu;
+        const uint32_t a0 = c0 & 0xFFu, a1 = (c0 >> 8) & 0xFFu, a2 = (c0 >> 16) & 0xFFu, a3 = c0 >> 24;
+        const uint32_t a4 = c1 & 0xFFu, a5 = (c1 >> 8) & 0xFFu, a6 = (c1 >> 16) & 0xFFu;
         const uint32_t m01 = max(a0, a1), m23 = max(a2, a3), m45 = max(a4, a5);
-        best = max(max(m01, m23), m45);
+        best = max(max(m01, m23), max(m45, a6));
         if (m01 == best) return (a0 >= a1) ? 0u : 1u;
         if (m23 == best) return (a2 >= a3) ? 2u : 3u;
-        return (a4 >= a5) ? 4u : 5u;
+        if (m45 == best) return (a4 >= a5) ? 4u : 5u;
+        return 6u;
     }
 };
 
@@ -57,14 +63,13 @@ struct Pool3Lane {
     uint32_t slot, meta, pxy;
     V3 o, x, nrm;
     bool alive;
+    uint32_t park; // a lane that is not alive: the ring its slot goes to (PK_HAND), or PK_IDLE
 };
 
 // ---- front half, kind REGEN: the path ended (background: raytrace.zig:82-86, or absorbed / depth limit: black); the
-//      item's next sample starts (raytrace.zig:170-176), or the item hands its sum over (:180-182) and the slot takes
-//      a new item from the global queue ----
+//      item's next sample starts (raytrace.zig:170-176), or, if it has none left, the slot moves to the PK_HAND ring ----
 template <int N>
-DI void pool3_front_regen(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, ItemQueue &iq, uint32_t total_items, uint32_t best,
-                          uint32_t lane, uint32_t lane_lt, uint32_t &n_bg, Pool3Lane &ln) {
+DI void pool3_front_regen(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, uint32_t best, uint32_t lane, uint32_t &n_bg, Pool3Lane &ln) {
     const uint32_t L = P.lanes;
     const uint32_t m = min(best, 32u);
     const bool active = lane < m;
@@ -73,65 +78,87 @@ DI void pool3_front_regen(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, Ite
     R.pop<PK_REGEN>(m);
     ln.slot = slot;
     ln.alive = false;
+    ln.park = PK_IDLE;
     ln.nrm = mk(0, 0, 0);
     ln.o = mk(P.ox, P.oy, P.oz);
     ln.x = mk(0, 0, 1);
-    uint32_t meta = 0, pxy = 0;
-    float ar = 0.0f, ag = 0.0f, ab = 0.0f;
-    if (active) {
-        const float4 a = S.A[slot];
-        const float4 c = S.C[slot];
+    ln.meta = 0;
+    ln.pxy = 0;
+    if (!active) return;
+    const float4 a = S.A[slot];
+    float4 c = S.C[slot];
+    const uint32_t meta = __float_as_uint(a.w);
+    const uint32_t pxy = __float_as_uint(S.B[slot].w);
+    if (meta & PM_BG) { // backgroundColor raytrace.zig:53-58 on the re-normalised direction (:54)
         const float2 dd = S.D[slot];
-        meta = __float_as_uint(a.w);
-        pxy = __float_as_uint(S.B[slot].w);
-        ar = c.w; ag = dd.x; ab = dd.y;
-        if (meta & PM_BG) { // backgroundColor raytrace.zig:53-58 on the re-normalised direction (:54)
-            const float udy = unit_y(mk(a.x, a.y, a.z));
-            n_bg++;
-            const float t = 0.5f * (udy + 1.0f);
-            const float it = 1.0f - t;
-            ar += c.x * (it + 0.5f * t);
-            ag += c.y * (it + 0.7f * t);
-            ab += c.z * (it + 1.0f * t);
-        }
-        const uint32_t nsamp = meta & PM_NSAMP_MASK;
-        if ((meta & PM_ITEM) && nsamp >= P.s_end) { // the item hands its sum over (raytrace.zig:180-182)
-            const uint32_t l = (nsamp - P.s_begin) & (L - 1u);
-            const uint32_t pixel = (pxy >> 16) * P.width + (pxy & 0xFFFFu);
-            float *out = P.out + ((size_t)l * P.width * P.height + pixel) * 3;
-            const float sc = (L == 1u) ? P.color_scale : 1.0f;
-            out[0] = ar * sc; out[1] = ag * sc; out[2] = ab * sc;
-            ar = ag = ab = 0.0f;
-            meta &= ~PM_ITEM;
-        }
+        const float udy = unit_y(mk(a.x, a.y, a.z));
+        n_bg++;
+        const float t = 0.5f * (udy + 1.0f);
+        const float it = 1.0f - t;
+        c.w += c.x * (it + 0.5f * t);
+        S.D[slot] = make_float2(dd.x + c.y * (it + 0.7f * t), dd.y + c.z * (it + 1.0f * t));
     }
-    const uint32_t want = __ballot_sync(0xffffffffu, active && !(meta & PM_ITEM));
-    if (want) { // warp-uniform
-        const uint32_t g = iq.take(P, total_items, want, lane, lane_lt);
-        if (g != ITEM_NONE) {
-            uint32_t l, px, py;
-            item_decode(P, g, l, px, py);
-            pxy = px | (py << 16);
-            S.B[slot].w = __uint_as_float(pxy);
-            meta = PM_ITEM | (P.s_begin + l);
-        }
-    }
-    if (active) {
-        if (meta & PM_ITEM) { // raytrace.zig:170-176
-            const uint32_t nsamp = meta & PM_NSAMP_MASK;
-            const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
-            const U4 r = rng_ctr(py * P.width + px, nsamp, 0u, P.seed32);
-            ln.x = primary_direction_raw(P, px, py, u01(r.x), u01(r.y));
-            S.C[slot] = make_float4(1.0f, 1.0f, 1.0f, ar);
-            S.D[slot] = make_float2(ag, ab);
-            meta = PM_ITEM | (nsamp + L); // bounce 0: the bookkeeping of the back half counts no reflection for this ray
-            ln.alive = true;
-        } else {
-            S.A[slot].w = __uint_as_float(0u); // the queue is exhausted: this slot goes idle
-        }
-    }
-    ln.meta = meta;
+    const uint32_t nsamp = meta & PM_NSAMP_MASK;
     ln.pxy = pxy;
+    if (nsamp >= P.s_end) { // no sample left: 32 such slots hand their sums over together (pool3_front_hand)
+        S.C[slot].w = c.w;
+        ln.park = PK_HAND;
+        return;
+    }
+    // raytrace.zig:170-176
+    const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
+    const U4 r = rng_ctr(py * P.width + px, nsamp, 0u, P.seed32);
+    ln.x = primary_direction_raw(P, px, py, u01(r.x), u01(r.y));
+    S.C[slot] = make_float4(1.0f, 1.0f, 1.0f, c.w);
+    ln.meta = PM_ITEM | (nsamp + L); // bounce 0: the bookkeeping of the back half counts no reflection for this ray
+    ln.alive = true;
+}
+
+// ---- front half, kind HAND: the item hands its sum over (raytrace.zig:180-182), the slot takes a new item from the global
+//      queue and starts its first sample.  A full batch draws ONE window of 32 consecutive items: the 32 slices of a pixel ----
+template <int N>
+DI void pool3_front_hand(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, ItemQueue &iq, uint32_t total_items, uint32_t best,
+                         uint32_t lane, uint32_t lane_lt, Pool3Lane &ln) {
+    const uint32_t L = P.lanes;
+    const uint32_t m = min(best, 32u);
+    const bool active = lane < m;
+    ZRT_PROF(46, active);
+    const uint32_t slot = S.ring[PK_HAND][(R.head<PK_HAND>() + lane) & 127u];
+    R.pop<PK_HAND>(m);
+    ln.slot = slot;
+    ln.alive = false;
+    ln.park = PK_IDLE;
+    ln.nrm = mk(0, 0, 0);
+    ln.o = mk(P.ox, P.oy, P.oz);
+    ln.x = mk(0, 0, 1);
+    ln.meta = 0;
+    ln.pxy = 0;
+    if (active && (__float_as_uint(S.A[slot].w) & PM_ITEM)) { // every slot starts here without an item
+        const uint32_t meta = __float_as_uint(S.A[slot].w), pxy = __float_as_uint(S.B[slot].w);
+        const float ar = S.C[slot].w;
+        const float2 dd = S.D[slot];
+        const uint32_t l = ((meta & PM_NSAMP_MASK) - P.s_begin) & (L - 1u);
+        const uint32_t pixel = (pxy >> 16) * P.width + (pxy & 0xFFFFu);
+        float *out = P.out + ((size_t)l * P.width * P.height + pixel) * 3;
+        const float sc = (L == 1u) ? P.color_scale : 1.0f;
+        out[0] = ar * sc; out[1] = dd.x * sc; out[2] = dd.y * sc;
+    }
+    const uint32_t g = iq.take(P, total_items, __ballot_sync(0xffffffffu, active), lane, lane_lt);
+    if (g != ITEM_NONE) {
+        uint32_t l, px, py;
+        item_decode(P, g, l, px, py);
+        const uint32_t pxy = px | (py << 16), nsamp = P.s_begin + l;
+        const U4 r = rng_ctr(py * P.width + px, nsamp, 0u, P.seed32); // raytrace.zig:170-176
+        ln.x = primary_direction_raw(P, px, py, u01(r.x), u01(r.y));
+        S.B[slot].w = __uint_as_float(pxy);
+        S.C[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        S.D[slot] = make_float2(0.0f, 0.0f);
+        ln.pxy = pxy;
+        ln.meta = PM_ITEM | (nsamp + L);
+        ln.alive = true;
+    } else if (active) {
+        S.A[slot].w = __uint_as_float(0u); // the queue is exhausted: this slot leaves the rings for good
+    }
 }
 
 // ---- front half, a hit of kind K: hit record + scatter (material.zig:43-51, hit_record.zig:28-41, sphere.zig:45-51) ----
@@ -147,6 +174,7 @@ DI void pool3_front_hit(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, uint3
     R.pop<K>(m);
     ln.slot = slot;
     ln.alive = false;
+    ln.park = PK_IDLE;
     ln.nrm = mk(0, 0, 0);
     ln.x = mk(0, 0, 1);
     ln.o = mk(0, 0, 0);
@@ -205,9 +233,9 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_pool3(const __grid_consta
     uint32_t n_refl = 0, n_bg = 0, n_depth = 0; // pixels, samples and rays: k_finish_counters (see K1)
 
     Pool3Rings R;
-    R.c0 = (uint32_t)N << (8 * PK_REGEN);
+    R.c1 = (uint32_t)N << (8 * (PK_HAND & 3u));
     for (uint32_t s = lane; s < (uint32_t)N; s += 32u) { // every slot starts without an item, waiting for one
-        S.ring[PK_REGEN][s] = (uint8_t)s;
+        S.ring[PK_HAND][s] = (uint8_t)s;
         S.A[s] = make_float4(0.0f, 0.0f, 1.0f, __uint_as_float(0u));
         S.C[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         S.D[s] = make_float2(0.0f, 0.0f);
@@ -222,7 +250,8 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_pool3(const __grid_consta
         if (best == 0) break; // every slot is idle: the global queue is exhausted and all paths have ended
         Pool3Lane ln;
         switch (k) { // warp-uniform
-        case PK_REGEN: pool3_front_regen<N>(P, S, R, iq, total_items, best, lane, lane_lt, n_bg, ln); break;
+        case PK_REGEN: pool3_front_regen<N>(P, S, R, best, lane, n_bg, ln); break;
+        case PK_HAND: pool3_front_hand<N>(P, S, R, iq, total_items, best, lane, lane_lt, ln); break;
         case PK_LAMB: pool3_front_hit<PK_LAMB, N>(P, S, R, best, lane, ln); break;
         case PK_METAL: pool3_front_hit<PK_METAL, N>(P, S, R, best, lane, ln); break;
         case PK_GLASS: pool3_front_hit<PK_GLASS, N>(P, S, R, best, lane, ln); break;
@@ -231,10 +260,10 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_pool3(const __grid_consta
         }
         // ---- back half, common: Ray.init normalises (ray.zig:11-13); bookkeeping of the scatter that produced this ray;
         //      the closest-hit query (raytrace.zig:71-81); classification ----
-        uint32_t next_kind = PK_IDLE;
+        uint32_t next_kind = ln.park;
         if (ln.alive) {
             ZRT_PROF(47, true);
-            const bool metal = k == PK_METAL || k == PK_METAL_IMG, primary = k == PK_REGEN; // warp-uniform
+            const bool metal = k == PK_METAL || k == PK_METAL_IMG, primary = k == PK_REGEN || k == PK_HAND; // warp-uniform
             uint32_t meta = ln.meta;
             const V3 dn = unit(ln.x);
             const bool absorbed = metal && !(dot(dn, ln.nrm) > 0.0f); // material.zig:90-95: black, no reflection counted
@@ -278,7 +307,7 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_pool3(const __grid_consta
                 }
             }
             R.c0 += __reduce_add_sync(0xffffffffu, add0);
-            if (P.pool_split) R.c1 += __reduce_add_sync(0xffffffffu, add1); // warp-uniform: rings 4, 5 exist only then
+            R.c1 += __reduce_add_sync(0xffffffffu, add1);
         }
         __syncwarp(); // slot state and ring entries written by one lane are read by another in the next iteration
     }
