@@ -340,6 +340,10 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         }
     }
     if (lanes > 32u) lanes = 32u;
+    // k_trace_pool3 parks a finished item until 32 of them hand over together, which pays when items are long: below ~12
+    // samples per item it takes 16 slices (125 spp per GPU of the 8-GPU split: 4.63 ms against 4.91 ms with 32; 250 spp:
+    // 8.85 against 8.97; profiles/r2_f_pool3_handover_policy_ab.log)
+    if (pool && p->sample_chunks == 0 && lanes == 32u && plan->n_samples < 384u) lanes = 16u;
     if (p->sample_chunks == 0) // the slice buffer is lanes x 12 B per pixel: keep the automatic choice under 2 GiB
         while (lanes > 1u && (uint64_t)p->width * p->height * 12ull * lanes > (2ull << 30)) lanes >>= 1;
     while (lanes & (lanes - 1u)) lanes &= lanes - 1u;          // round down to a power of two
