@@ -58,9 +58,9 @@ def algorithmic_ops(stats, counters):
 # under a profiler is only ever used for these fields): dram bytes read + written, l1tex / lts bytes, issue-slot
 # utilisation and active lanes per instruction.  Filled from profiles/ by hand after each capture.
 NCU = {
-    "c5": {"traffic": 92832000 + 416680192, "issue_active_pct": 81.1, "active_lanes": 27.16,
-           "source": "profiles/r2_c_c5_pool3_summary.txt (1 GPU, k_trace_pool3<7,128,7>, 100 spp launch: the 32 partial-sum slices are the "
-                     "same 384 MB at any sample count)"},
+    "c5": {"traffic": 81351424 + 403899904, "issue_active_pct": 83.2, "active_lanes": 26.89,
+           "source": "profiles/r2_e_c5_pool3_hand_summary.txt (1 GPU, k_trace_pool3<7,128,7>, the full 1000 spp launch; 384 MB of the "
+                     "writes are the 32 partial-sum slices)"},
     "c2": {"traffic": 14648832 + 63718656, "issue_active_pct": 76.9, "active_lanes": 17.59,
            "source": "profiles/r2_c_c2_warp_summary.txt (k_trace_ws, 64 spp launch)"},
     "c3": {"traffic": 35642112 + 393396480, "issue_active_pct": 70.2, "active_lanes": 21.82,
@@ -328,7 +328,7 @@ def kernel_name_for(wl_name, flags):
         wl = WORKLOADS[wl_name]
         auto_pool = wl["w"] * wl["h"] * wl["spp"] >= (1 << 24)  # the library's rule for sphere-only scenes (zrt_api.cu makePlan)
         pool = (flags & A.ZRT_FLAG_KERNEL_POOL or auto_pool) and not flags & A.ZRT_FLAG_KERNEL_THREAD
-        return "k_trace_pool<7,128,7>" if pool else "k_trace<SPHERES,7>"
+        return "k_trace_pool3<7,128,7>" if pool else "k_trace<SPHERES,7>"
     return "k_trace_ws / k_trace<BVH>"
 
 
