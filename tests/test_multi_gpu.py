@@ -54,6 +54,31 @@ def test_group_of_one_is_zrt_render():
                 grp.render(cam, bad)
 
 
+@pytest.mark.gpu
+def test_reload_swaps_the_scene_on_every_local_device():
+    """zrt_multi_reload: a new scene for the same group (communicator and accumulators kept), created on one host thread per
+    local device; what bench.py's end-to-end leg does every step."""
+    n = min(Z.device_count(), 4)
+    sc_a, cam_a = scenes_py.three_balls()
+    sc_b, cam_b = scenes_py.small_test_scene()
+    p = A.make_params(80, 60, 9, 30, x_limit=A.ZRT_XLIMIT_WIDTH)
+    with Z.Scene(sc_a, device=0) as da, Z.Scene(sc_b, device=0) as db:
+        img_a, c_a, _ = da.render(cam_a, p)
+        img_b, c_b, _ = db.render(cam_b, p)
+    with Z.MultiScene(sc_a, devices=list(range(n))) as grp:
+        img, c, _ = grp.render(cam_a, p)
+        assert c.as_dict() == c_a.as_dict()
+        for _ in range(2):
+            grp.reload(sc_b)
+            img, c, _ = grp.render(cam_b, p)
+            assert c.as_dict() == c_b.as_dict()
+            np.testing.assert_allclose(img, img_b, rtol=1e-5, atol=1e-6)
+            grp.reload(sc_a)
+            img, c, _ = grp.render(cam_a, p)
+            assert c.as_dict() == c_a.as_dict()
+            np.testing.assert_allclose(img, img_a, rtol=1e-5, atol=1e-6)
+
+
 def _worlds():
     n = Z.device_count()
     return [w for w in (2, 3, 4, 8) if w <= n]
