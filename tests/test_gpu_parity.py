@@ -192,7 +192,10 @@ def test_pool_kernels_every_slot_count(built, name, w, spp, depth, monkeypatch):
             monkeypatch.setenv("ZRT_POOL_SLOTS", slots)
             img_p, c_p, _ = dev.render(cam, A.make_params(w, w, spp, depth, sample_chunks=chunks, flags=A.ZRT_FLAG_KERNEL_POOL))
             _counters_equal(c_t, c_p)
-            assert np.array_equal(img_t.view(np.uint32), img_p.view(np.uint32)), (name, chunks, slots)
+            if chunks:  # pinned slice count: the same f32 sums in the same order
+                assert np.array_equal(img_t.view(np.uint32), img_p.view(np.uint32)), (name, chunks, slots)
+            else:  # every kernel picks its own slice count: same paths, the sum re-associated
+                np.testing.assert_allclose(img_p, img_t, rtol=1e-5, atol=1e-6)
     monkeypatch.delenv("ZRT_POOL_SLOTS")
 
 

@@ -53,7 +53,9 @@ def main():
                         ok_i = np.allclose(img, img_o, rtol=2e-5, atol=1e-6)
                         if ref is None:
                             ref = img
-                        ok_b = np.array_equal(ref.view(np.uint32), img.view(np.uint32))
+                        # pinned slice counts: the same f32 sums in the same order, bit for bit.  chunks = 0: every kernel picks
+                        # its own slice count (k_trace_pool3 takes 16 below 384 spp), so only the association may differ
+                        ok_b = np.array_equal(ref.view(np.uint32), img.view(np.uint32)) if chunks else np.allclose(ref, img, rtol=1e-5, atol=1e-6)
                         bad += not (ok_c and ok_i and ok_b)
                         print(f"{name:14s} chunks={chunks} {kname:6s} {slots:4s} counters={'ok' if ok_c else 'DIFF'} "
                               f"oracle={'ok' if ok_i else 'DIFF'} bits={'ok' if ok_b else 'DIFF'} rays={c.rays_processed} {dt:.1f}s", flush=True)

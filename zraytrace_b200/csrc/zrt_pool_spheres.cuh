@@ -63,11 +63,24 @@ struct Pool3Lane {
     uint32_t slot, meta, pxy;
     V3 o, x, nrm;
     bool alive;
-    uint32_t park; // a lane that is not alive: the ring its slot goes to (PK_HAND), or PK_IDLE
+    uint32_t park; // a lane that is not alive: PK_IDLE (its slot leaves the rings)
 };
 
-// ---- front half, kind REGEN: the path ended (background: raytrace.zig:82-86, or absorbed / depth limit: black); the
-//      item's next sample starts (raytrace.zig:170-176), or, if it has none left, the slot moves to the PK_HAND ring ----
+// backgroundColor (raytrace.zig:53-58) on the re-normalised direction (:54) of a path that left the scene, added to the item's
+// sum (raytrace.zig:177): acc (r in c.w, g and b in S.D) += throughput * colour
+template <int N>
+DI void pool3_add_background(PoolSlots3<N> &S, uint32_t slot, const float4 &a, float4 &c, uint32_t &n_bg) {
+    const float2 dd = S.D[slot];
+    const float udy = unit_y(mk(a.x, a.y, a.z));
+    n_bg++;
+    const float t = 0.5f * (udy + 1.0f);
+    const float it = 1.0f - t;
+    c.w += c.x * (it + 0.5f * t);
+    S.D[slot] = make_float2(dd.x + c.y * (it + 0.7f * t), dd.y + c.z * (it + 1.0f * t));
+}
+
+// ---- front half, kind REGEN: the path ended (background: raytrace.zig:82-86, or absorbed / depth limit: black) and the
+//      item has a sample left (the back half sends the others straight to PK_HAND): the next sample starts (:170-176) ----
 template <int N>
 DI void pool3_front_regen(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, uint32_t best, uint32_t lane, uint32_t &n_bg, Pool3Lane &ln) {
     const uint32_t L = P.lanes;
@@ -89,22 +102,9 @@ DI void pool3_front_regen(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, uin
     float4 c = S.C[slot];
     const uint32_t meta = __float_as_uint(a.w);
     const uint32_t pxy = __float_as_uint(S.B[slot].w);
-    if (meta & PM_BG) { // backgroundColor raytrace.zig:53-58 on the re-normalised direction (:54)
-        const float2 dd = S.D[slot];
-        const float udy = unit_y(mk(a.x, a.y, a.z));
-        n_bg++;
-        const float t = 0.5f * (udy + 1.0f);
-        const float it = 1.0f - t;
-        c.w += c.x * (it + 0.5f * t);
-        S.D[slot] = make_float2(dd.x + c.y * (it + 0.7f * t), dd.y + c.z * (it + 1.0f * t));
-    }
+    if (meta & PM_BG) pool3_add_background<N>(S, slot, a, c, n_bg);
     const uint32_t nsamp = meta & PM_NSAMP_MASK;
     ln.pxy = pxy;
-    if (nsamp >= P.s_end) { // no sample left: 32 such slots hand their sums over together (pool3_front_hand)
-        S.C[slot].w = c.w;
-        ln.park = PK_HAND;
-        return;
-    }
     // raytrace.zig:170-176
     const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
     const U4 r = rng_ctr(py * P.width + px, nsamp, 0u, P.seed32);
@@ -118,7 +118,7 @@ DI void pool3_front_regen(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, uin
 //      queue and starts its first sample.  A full batch draws ONE window of 32 consecutive items: the 32 slices of a pixel ----
 template <int N>
 DI void pool3_front_hand(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, ItemQueue &iq, uint32_t total_items, uint32_t best,
-                         uint32_t lane, uint32_t lane_lt, Pool3Lane &ln) {
+                         uint32_t lane, uint32_t lane_lt, uint32_t &n_bg, Pool3Lane &ln) {
     const uint32_t L = P.lanes;
     const uint32_t m = min(best, 32u);
     const bool active = lane < m;
@@ -134,14 +134,16 @@ DI void pool3_front_hand(const KParams &P, PoolSlots3<N> &S, Pool3Rings &R, Item
     ln.meta = 0;
     ln.pxy = 0;
     if (active && (__float_as_uint(S.A[slot].w) & PM_ITEM)) { // every slot starts here without an item
-        const uint32_t meta = __float_as_uint(S.A[slot].w), pxy = __float_as_uint(S.B[slot].w);
-        const float ar = S.C[slot].w;
+        const float4 a = S.A[slot];
+        float4 c = S.C[slot];
+        const uint32_t meta = __float_as_uint(a.w), pxy = __float_as_uint(S.B[slot].w);
+        if (meta & PM_BG) pool3_add_background<N>(S, slot, a, c, n_bg); // the item's last path left the scene
         const float2 dd = S.D[slot];
         const uint32_t l = ((meta & PM_NSAMP_MASK) - P.s_begin) & (L - 1u);
         const uint32_t pixel = (pxy >> 16) * P.width + (pxy & 0xFFFFu);
         float *out = P.out + ((size_t)l * P.width * P.height + pixel) * 3;
         const float sc = (L == 1u) ? P.color_scale : 1.0f;
-        out[0] = ar * sc; out[1] = dd.x * sc; out[2] = dd.y * sc;
+        out[0] = c.w * sc; out[1] = dd.x * sc; out[2] = dd.y * sc;
     }
     const uint32_t g = iq.take(P, total_items, __ballot_sync(0xffffffffu, active), lane, lane_lt);
     if (g != ITEM_NONE) {
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_pool3(const __grid_consta
         Pool3Lane ln;
         switch (k) { // warp-uniform
         case PK_REGEN: pool3_front_regen<N>(P, S, R, best, lane, n_bg, ln); break;
-        case PK_HAND: pool3_front_hand<N>(P, S, R, iq, total_items, best, lane, lane_lt, ln); break;
+        case PK_HAND: pool3_front_hand<N>(P, S, R, iq, total_items, best, lane, lane_lt, n_bg, ln); break;
         case PK_LAMB: pool3_front_hit<PK_LAMB, N>(P, S, R, best, lane, ln); break;
         case PK_METAL: pool3_front_hit<PK_METAL, N>(P, S, R, best, lane, ln); break;
         case PK_GLASS: pool3_front_hit<PK_GLASS, N>(P, S, R, best, lane, ln); break;
@@ -274,7 +276,9 @@ __global__ void __launch_bounds__(128, BLOCKS) k_trace_pool3(const __grid_consta
             n_depth += exhausted ? 1u : 0u;
             meta &= ~((7u << PM_HIT_SHIFT) | PM_BG);
             if (primary) meta += 1u << PM_BOUNCE_SHIFT; // the primary ray is ray 1
-            next_kind = PK_REGEN;
+            // a path that ends now: next sample in a REGEN batch, or - no sample left (meta holds the NEXT sample index) - the
+            // hand-over ring directly, so that no REGEN lane is spent on noticing it
+            next_kind = ((meta & PM_NSAMP_MASK) >= P.s_end) ? PK_HAND : PK_REGEN;
             if (!(absorbed || exhausted)) {
                 Hit h;
                 ZRT_PROF(primary ? 48 : 49, true);
