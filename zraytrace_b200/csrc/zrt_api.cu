@@ -431,9 +431,9 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         }
     // k_trace_pool (K1q): spheres-only scenes, bounce count and pixel coordinates packed in 16 bits each
     P.inl_kinds = 0;
-    P.rows_top_down = 1; // the item queue runs from the top scanline down: 0.8 % (1000 spp) to 1.3 % (125 spp) faster on C5 than bottom up
-                         // with either sphere kernel (profiles/r2_j_row_order_ab.log); results do not depend on the order
-    if (const char *e = std::getenv("ZRT_ROWS_TOP_DOWN")) P.rows_top_down = std::atoi(e) ? 1u : 0u;
+    P.row_order = 1; // the item queue runs from the top scanline down: 0.8-1.3 % faster than bottom up on C5 with either sphere
+                     // kernel, 10.5 / 2.7 / 3.0 % on C2 / C3 / C4 (profiles/r2_k_tail_and_row_order_ab.log); results do not depend on it
+    if (const char *e = std::getenv("ZRT_ROW_ORDER")) P.row_order = (uint32_t)std::atoi(e) & 3u; // A/B hook
     P.pool_split = 0; // C5: 34.34 ms without the image rings, 34.60 ms with them (profiles/r2_c_pool3_ab.log)
     if (const char *e = std::getenv("ZRT_POOL_SPLIT")) P.pool_split = std::atoi(e) ? 1u : 0u; // A/B hook
     if (r->mode == MODE_SPHERES)
