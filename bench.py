@@ -58,15 +58,15 @@ def algorithmic_ops(stats, counters):
 # under a profiler is only ever used for these fields): dram bytes read + written, l1tex / lts bytes, issue-slot
 # utilisation and active lanes per instruction.  Filled from profiles/ by hand after each capture.
 NCU = {
-    "c5": {"traffic": 81351424 + 403899904, "issue_active_pct": 83.2, "active_lanes": 26.89,
-           "source": "profiles/r2_e_c5_pool3_hand_summary.txt (1 GPU, k_trace_pool3<7,128,7>, the full 1000 spp launch; 384 MB of the "
+    "c5": {"traffic": 71932672 + 392275456, "issue_active_pct": 83.7, "active_lanes": 27.25,
+           "source": "profiles/r2_w_c5_pool3_final_summary.txt (1 GPU, k_trace_pool3<7,128,7>, the full 1000 spp launch; 384 MB of the "
                      "writes are the 32 partial-sum slices)"},
-    "c2": {"traffic": 14648832 + 63718656, "issue_active_pct": 76.9, "active_lanes": 17.59,
-           "source": "profiles/r2_c_c2_warp_summary.txt (k_trace_ws, 64 spp launch)"},
-    "c3": {"traffic": 35642112 + 393396480, "issue_active_pct": 70.2, "active_lanes": 21.82,
-           "source": "profiles/r2_c_c3_warp_summary.txt (k_trace_ws, 32 spp launch)"},
-    "c4": {"traffic": 89412864 + 392858112, "issue_active_pct": 72.5, "active_lanes": 21.11,
-           "source": "profiles/r2_c_c4_warp_summary.txt (k_trace_ws, 16 spp launch)"},
+    "c2": {"traffic": 6677248 + 61849856, "issue_active_pct": 78.9, "active_lanes": 17.61,
+           "source": "profiles/r2_w_c2_ws_final_summary.txt (k_trace_ws, the full 256 spp launch)"},
+    "c3": {"traffic": 21672960 + 380491776, "issue_active_pct": 82.5, "active_lanes": 20.41,
+           "source": "profiles/r2_w_c3_ws_final_summary.txt (k_trace_ws, 128 spp launch: the 32 slices are the same 403 MB at any sample count)"},
+    "c4": {"traffic": 124312064 + 796394240, "issue_active_pct": 79.1, "active_lanes": 20.33,
+           "source": "profiles/r2_w_c4_ws_final_summary.txt (k_trace_ws, 128 spp launch: the 32 slices are the same 796 MB at any sample count)"},
 }
 
 
