@@ -199,6 +199,23 @@ def test_pool_kernels_every_slot_count(built, name, w, spp, depth, monkeypatch):
     monkeypatch.delenv("ZRT_POOL_SLOTS")
 
 
+@pytest.mark.parametrize("name,w,h,spp", [("three_balls", 75, 41, 9), ("teapot", 48, 64, 6)])
+def test_results_do_not_depend_on_the_scanline_order_of_the_queue(built, name, w, h, spp, monkeypatch):
+    """The item queue visits the scanlines top-down by default (ZRT_ROW_ORDER: 0 bottom-up as the reference's loop, 1 top-down,
+    2 middle-out, 3 edges-in).  Every item is independent, so counters and image bits are those of any other order."""
+    sc, cam, dev = built(name)
+    ref = None
+    for order in ("1", "0", "2", "3"):
+        monkeypatch.setenv("ZRT_ROW_ORDER", order)
+        for flag in (A.ZRT_FLAG_KERNEL_THREAD, A.ZRT_FLAG_KERNEL_WARP, A.ZRT_FLAG_KERNEL_POOL):
+            img, c, _ = dev.render(cam, A.make_params(w, h, spp, 30, sample_chunks=4, flags=flag, x_limit=A.ZRT_XLIMIT_WIDTH))
+            if ref is None:
+                ref = (img, c)
+            _counters_equal(ref[1], c)
+            assert np.array_equal(ref[0].view(np.uint32), img.view(np.uint32)), (name, order, flag)
+    monkeypatch.delenv("ZRT_ROW_ORDER")
+
+
 def test_reference_topology_full_paths(built):
     sc, cam, dev = built("teapot")
     p = A.make_params(64, 64, 8, 30, sample_chunks=1)
