@@ -434,6 +434,20 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.row_order = 1; // the item queue runs from the top scanline down: 0.8-1.3 % faster than bottom up on C5 with either sphere
                      // kernel, 10.5 / 2.7 / 3.0 % on C2 / C3 / C4 (profiles/r2_k_tail_and_row_order_ab.log); results do not depend on it
     if (const char *e = std::getenv("ZRT_ROW_ORDER")) P.row_order = (uint32_t)std::atoi(e) & 3u; // A/B hook
+    // k_trace_pool3 draws windows of 4 pixels' worth of items (128 at 32 slices, 64 at 16): the 128 slots of a warp then sit on
+    // neighbouring pixels instead of on whatever 4 windows the ~4000 resident warps left it, and its batches of primary rays
+    // stay coherent.  Measured on C5 (profiles/r2_x_pool3_queue_window_fine_ab.log): 32 / 64 / 96 / 128 / 160 items -> 32.88 /
+    // 32.45 / 32.18 / 32.12 / 32.02 ms at 1000 spp, smooth; beyond ~200 items (more than a pool holds) it turns erratic and
+    // slower (256: 33.7, 384: 35).  The last round of windows before the queue ends is 32 items again.
+    P.queue_window = 32;
+    P.queue_taper = 0;
+    if (pool && r->mode == MODE_SPHERES) {
+        uint32_t win = 4u * lanes;
+        win = win < 32u ? 32u : (win > 128u ? 128u : win);
+        if (const char *e = std::getenv("ZRT_QUEUE_WINDOW")) win = (uint32_t)std::atoi(e) & ~31u; // A/B hook
+        const uint64_t items = pixels * lanes, round = 148ull * 28ull * win * 2ull;
+        if (win > 32u && items > round) { P.queue_window = win; P.queue_taper = (uint32_t)(items - round); }
+    }
     P.pool_split = 0; // C5: 34.34 ms without the image rings, 34.60 ms with them (profiles/r2_c_pool3_ab.log)
     if (const char *e = std::getenv("ZRT_POOL_SPLIT")) P.pool_split = std::atoi(e) ? 1u : 0u; // A/B hook
     if (r->mode == MODE_SPHERES)

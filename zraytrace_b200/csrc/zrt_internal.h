@@ -149,6 +149,7 @@ struct KParams {
     uint32_t two_paths; // 1: k_trace_x2
     uint32_t pool;      // spheres-only scenes: slots per warp of k_trace_pool (0 = k_trace)
     uint32_t inl_kinds; // k_trace_pool: shade ring (PoolKind) of inline sphere i in bits 3i .. 3i+2
+    uint32_t queue_window, queue_taper; // items a warp draws from the global queue per atomic (32, or more while the counter is below queue_taper)
     uint32_t row_order; // scanline order of the item queue: 0 bottom up, 1 top down, 2 middle outwards, 3 edges inwards
     uint32_t pool_split; // 1: image-textured Lambertian / metal spheres have rings of their own (PK_LAMB_IMG, PK_METAL_IMG)
     SpherePair inl_prim[MAX_INLINE_SPHERES / 2]; // rays from the camera origin: (oc.x, oc.y, oc.z, -(|oc|^2 - r^2)) per sphere
