@@ -443,10 +443,11 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     P.queue_taper = 0;
     if (pool && r->mode == MODE_SPHERES) {
         uint32_t win = 4u * lanes;
-        win = win < 32u ? 32u : (win > 128u ? 128u : win);
-        if (const char *e = std::getenv("ZRT_QUEUE_WINDOW")) win = (uint32_t)std::atoi(e) & ~31u; // A/B hook
-        const uint64_t items = pixels * lanes, round = 148ull * 28ull * win * 2ull;
-        if (win > 32u && items > round) { P.queue_window = win; P.queue_taper = (uint32_t)(items - round); }
+        win = win < 64u ? 64u : (win > 128u ? 128u : win); // 8 slices at 2000^2: 64 items 32.4 ms, 32 items 32.9 ms
+        const uint64_t items = pixels * lanes, warps = 148ull * 28ull;
+        bool on = items >= warps * win * 48ull; // a warp should see ~50 windows or the coarser hand-out costs balance (500^2: 2.8 against 2.4 ms)
+        if (const char *e = std::getenv("ZRT_QUEUE_WINDOW")) { win = (uint32_t)std::atoi(e) & ~31u; on = win > 32u && items > warps * win * 2ull; } // A/B hook
+        if (on) { P.queue_window = win; P.queue_taper = (uint32_t)(items - warps * win * 2ull); }
     }
     P.pool_split = 0; // C5: 34.34 ms without the image rings, 34.60 ms with them (profiles/r2_c_pool3_ab.log)
     if (const char *e = std::getenv("ZRT_POOL_SPLIT")) P.pool_split = std::atoi(e) ? 1u : 0u; // A/B hook
