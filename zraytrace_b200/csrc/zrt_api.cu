@@ -441,6 +441,14 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     // slower (256: 33.7, 384: 35).  The last round of windows before the queue ends is 32 items again.
     P.queue_window = 32;
     P.queue_taper = 0;
+    if (r->mode == MODE_BVH && !pool) { // k_trace_ws / k_trace on BVH scenes: two pixels' worth per atomic.  C2 / C3 / C4: 7.97 / 32.85 /
+        // 86.4 ms at 32 items, 7.81 / 32.19 / 85.0 at 64; 128 and more make the end of the launch depend on which warp drew the
+        // heaviest pixels (C4: 87-95 ms at 128, 103 at 256; profiles/r2_aa_bvh_queue_window_ab.log)
+        uint32_t win = 64;
+        if (const char *e = std::getenv("ZRT_QUEUE_WINDOW_ALL")) win = (uint32_t)std::atoi(e) & ~31u; // A/B hook
+        const uint64_t items = pixels * lanes, warps = 148ull * 32ull;
+        if (win > 32u && lanes == 32u && items >= warps * win * 48ull) { P.queue_window = win; P.queue_taper = (uint32_t)(items - warps * win * 2ull); }
+    }
     if (pool && r->mode == MODE_SPHERES) {
         uint32_t win = 4u * lanes;
         win = win < 64u ? 64u : (win > 128u ? 128u : win); // 8 slices at 2000^2: 64 items 32.4 ms, 32 items 32.9 ms
