@@ -447,7 +447,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
         uint32_t win = 64;
         if (const char *e = std::getenv("ZRT_QUEUE_WINDOW_ALL")) win = (uint32_t)std::atoi(e) & ~31u; // A/B hook
         const uint64_t items = pixels * lanes, warps = 148ull * 32ull;
-        if (win > 32u && lanes == 32u && items >= warps * win * 48ull) { P.queue_window = win; P.queue_taper = (uint32_t)(items - warps * win * 2ull); }
+        if (win > 32u && lanes == 32u && items >= warps * win * 24ull) { P.queue_window = win; P.queue_taper = (uint32_t)(items - warps * win * 2ull); }
     }
     if (pool && r->mode == MODE_SPHERES) {
         uint32_t win = 4u * lanes;
