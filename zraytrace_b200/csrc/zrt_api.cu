@@ -349,7 +349,7 @@ int makePlan(zrt_scene *sc, const zrt_camera *cam, const zrt_params *p, DevRep *
     while (lanes & (lanes - 1u)) lanes &= lanes - 1u;          // round down to a power of two
     while (lanes > 1u && lanes > plan->n_samples) lanes >>= 1; // every slice gets at least one sample
     if (lanes < 1u) lanes = 1u;
-    if (pixels * lanes > 0xFFFFFF00ull) return fail(ZRT_ERR_INVALID, "image too large");
+    if (pixels * lanes > 0xFFF00000ull) return fail(ZRT_ERR_INVALID, "image too large"); // the item counter is 32 bits and every resident warp overshoots it once by one window
     P.lanes = lanes;
     P.lanes_log2 = 0;
     while ((1u << P.lanes_log2) < lanes) P.lanes_log2++;
