@@ -104,7 +104,11 @@ struct RefTree {
     // atomically), so the top levels of the recursion fan out over host threads.  The tree is the same
     // tree; only the node numbering (never observable) depends on timing.
     static constexpr uint32_t kParallelDepth = 4;
-    static constexpr size_t kParallelMin = 768; // a thread costs ~20 us: worth it from a few hundred primitives per half (teapot, 6 k triangles: build 8.3 -> 3 ms)
+    // A half of a split gets its own thread from this many primitives on: 8192 on large meshes (at most 64 threads are created per
+    // build and they must go to the large subtrees: 322 k triangles with a fixed 768 cost +55 ms), down to 768 on small ones, where a
+    // thread's ~20 us is still a fraction of the half's work (teapot, 6 k triangles: c2 end to end 12.4 -> 11.2 ms)
+    static size_t parallelMin(size_t n_total) { return std::max<size_t>(768, std::min<size_t>(8192, n_total / 8)); }
+    static constexpr size_t kParallelMin = 8192; // the literal (sort in the recursion) rebuild, by depth
 
     explicit RefTree(const HostScene &s) : sc(s) {
         const size_t n = sc.surfaces.size();
@@ -372,7 +376,7 @@ struct RefTree {
         const size_t at = ss.best_split;
         partitionLists(lo, n, final_order, at);
         int32_t l, r;
-        if (std::min(at, n - at) >= kParallelMin && spawned.fetch_add(1) < 64) {
+        if (std::min(at, n - at) >= parallelMin(sc.surfaces.size()) && spawned.fetch_add(1) < 64) {
             Worker left([&] { l = dividePresorted(lo, at, final_order, child_x, depth + 1); });
             r = dividePresorted(lo + at, n - at, final_order, child_x, depth + 1);
             left.join();
@@ -516,6 +520,7 @@ struct SahBuilder {
     std::atomic<uint32_t> max_depth{0};
     std::atomic<uint32_t> spawned{0};
     Raw<float> cen[3];
+    size_t par_min = 8192; // RefTree::parallelMin(primitives)
 
     static float area(const Box &b) {
         const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
@@ -652,7 +657,7 @@ struct SahBuilder {
         // SAH splits are uneven (a ground sphere, a small mesh next to a big one), so the fan-out over host threads goes
         // by subtree size, not by depth; `spawned` bounds the number of threads ever created per build
         const size_t small = std::min(mid, n - mid);
-        if (small >= RefTree::kParallelMin && spawned.fetch_add(1) < 64) {
+        if (small >= par_min && spawned.fetch_add(1) < 64) {
             Worker left([&] { l = build(ids, mid, depth + 1, my + 1); });
             r = build(ids + mid, n - mid, depth + 1, my + (uint32_t)mid);
             left.join();
@@ -723,6 +728,7 @@ void build_flat_bvh(const HostScene &scene, bool sah, FlatBvh *out) {
         out->nodes.clear();
         out->nodes.resize(m - 1);
         SahBuilder sb{pbox.data(), pref.data(), &out->nodes, {}, {}, {}};
+        sb.par_min = RefTree::parallelMin(m);
         for (int k = 0; k < 3; k++) sb.cen[k].alloc(m);
         parallelFor(m, 16384, [&](size_t begin, size_t end) {
             for (size_t i = begin; i < end; i++) {
